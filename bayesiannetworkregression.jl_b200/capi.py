@@ -1,0 +1,92 @@
+"""ctypes binding of include/bnr.h -- one prototype per exported symbol, nothing else."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbnr.so")
+
+
+class BnrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbnr error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    """struct bnr_params (include/bnr.h)."""
+    _fields_ = [("n", C.c_int32), ("V", C.c_int32), ("R", C.c_int32), ("num_chains", C.c_int32),
+                ("chain_offset", C.c_int32), ("device", C.c_int32), ("trace_full_chains", C.c_int32),
+                ("trace_gamma_xi_all", C.c_int32), ("trace_rows", C.c_int64), ("seed", C.c_uint64),
+                ("eta", C.c_double), ("zeta", C.c_double), ("iota", C.c_double), ("a_delta", C.c_double),
+                ("b_delta", C.c_double), ("nu", C.c_double), ("gig_inject_len", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+VAR = dict(tau2=0, u=1, xi=2, gamma=3, S=4, theta=5, Delta=6, M=7, mu=8, lam=9, pi=10)
+COND = dict(tau2=0, u_xi=1, gamma=2, D=3, theta=4, Delta=5, M=6, mu=7, lam=8, pi=9)
+AUX = dict(tau2_params=0, sigma_inv=1, sigma_chol=2, mu_t=3, log_odds=4, W=5, G=6, G_chol=7, rhs=8, a4=9, chi=10,
+           theta_params=11, delta_params=12, m_params=13, mu_params=14, lambda_logw=15, lambda_weights=16,
+           pi_alpha=17, gig_used=18)
+STATUS_BITS = dict(jitter=1, sigma_notpd=2, g_notpd=4, gig_cap=8, inj_exhausted=16, nan=32, psi_notpd=64)
+
+_H = C.c_void_p
+_DP = C.POINTER(C.c_double)
+_I64P = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes): every symbol include/bnr.h declares
+PROTOTYPES = {
+    "bnr_version": (C.c_int, []),
+    "bnr_last_error": (C.c_char_p, []),
+    "bnr_default_params": (None, [C.POINTER(Params)]),
+    "bnr_create": (C.c_int, [C.POINTER(Params), _DP, _DP, C.POINTER(_H)]),
+    "bnr_destroy": (C.c_int, [_H]),
+    "bnr_init_state": (C.c_int, [_H]),
+    "bnr_run": (C.c_int, [_H, C.c_int64]),
+    "bnr_sync": (C.c_int, [_H]),
+    "bnr_iteration": (C.c_int, [_H, _I64P]),
+    "bnr_last_run_ms": (C.c_int, [_H, C.POINTER(C.c_float)]),
+    "bnr_set_trace_row": (C.c_int, [_H, C.c_int64]),
+    "bnr_get_trace_row": (C.c_int, [_H, _I64P]),
+    "bnr_copy_trace_rows": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
+    "bnr_set_moment_window": (C.c_int, [_H, C.c_int64, C.c_int64]),
+    "bnr_moments_device": (C.c_int, [_H, C.POINTER(C.c_void_p), _I64P]),
+    "bnr_rhat_from_moments": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _DP, _DP]),
+    "bnr_moments_from_trace": (C.c_int, [_H, C.c_int64, C.c_int64]),
+    "bnr_moment_half_len": (C.c_int, [_H, _I64P]),
+    "bnr_rhat": (C.c_int, [_H, _DP, _DP]),
+    "bnr_get_state": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
+    "bnr_set_state": (C.c_int, [_H, C.c_int32, C.c_int32, _DP]),
+    "bnr_var_size": (C.c_int, [_H, C.c_int32, _I64P]),
+    "bnr_get_trace": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _DP]),
+    "bnr_status": (C.c_int, [_H, C.POINTER(C.c_int32)]),
+    "bnr_set_injection": (C.c_int, [_H, _DP, C.c_int64]),
+    "bnr_injection_size": (C.c_int, [_H, C.c_int32, _I64P]),
+    "bnr_step": (C.c_int, [_H, C.c_int32]),
+    "bnr_finish_sweep": (C.c_int, [_H]),
+    "bnr_enable_aux": (C.c_int, [_H, C.c_int32]),
+    "bnr_get_aux": (C.c_int, [_H, C.c_int32, C.c_int32, _DP, C.c_int64]),
+    "bnr_rng_stream": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _DP]),
+    "bnr_rng_gamma": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_int32, _DP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libbnr.so (built in-tree by `make` / __graft_entry__.build()).  Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libbnr.so not found at %s: build it with `make` (there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise BnrError(code, lib().bnr_last_error().decode("utf8", "replace"))

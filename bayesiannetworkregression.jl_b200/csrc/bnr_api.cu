@@ -1,0 +1,747 @@
+// C ABI of libbnr (see include/bnr.h): handle life-cycle, the sweep schedule (one CUDA graph per sweep),
+// state / trace access in reference layout, streaming R-hat, and the parity-test hooks.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/bnr.h"
+#include "bnr_engine.cuh"
+#include "bnr_kernels.h"
+
+static_assert(BNR_ST_JITTER == BNR_ST_JITTER_ && BNR_ST_SIGMA_NOTPD == BNR_ST_SIGMA_NOTPD_ &&
+              BNR_ST_G_NOTPD == BNR_ST_G_NOTPD_ && BNR_ST_GIG_CAP == BNR_ST_GIG_CAP_ &&
+              BNR_ST_INJ_EXHAUSTED == BNR_ST_INJ_EXHAUSTED_ && BNR_ST_NAN == BNR_ST_NAN_ &&
+              BNR_ST_PSI_NOTPD == BNR_ST_PSI_NOTPD_, "status bits out of sync");
+static_assert(BNR_COND_THETA == BNR_COND_THETA_ && BNR_COND_DELTA == BNR_COND_DELTA_ && BNR_COND_M == BNR_COND_M_ &&
+              BNR_COND_MU == BNR_COND_MU_ && BNR_COND_LAMBDA == BNR_COND_LAMBDA_ && BNR_COND_PI == BNR_COND_PI_,
+              "conditional ids out of sync");
+static_assert(BNR_MAX_R == bnr::MAX_R, "MAX_R out of sync");
+
+using namespace bnr;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (call);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(_e == cudaErrorMemoryAllocation ? BNR_ENOMEM : BNR_ECUDA,                              \
+                  std::string(#call) + ": " + cudaGetErrorString(_e));                                   \
+  } while (0)
+
+struct bnr_handle {
+  bnr_params p;
+  Engine e;
+  cudaStream_t stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<void*> allocs;
+  double* ws = nullptr;          // split-K workspace
+  double* d_inj = nullptr;       // injected variates
+  long long inj_len = 0;
+  bool aux_on = false;
+  Aux aux_saved = {};
+  long long mom_half = 0;        // draws per split chain behind the current moments buffer
+  bool xg_valid = false;         // e.xg == X * gamma for the current state
+  bool ran = false;
+  double* d_rhat = nullptr;      // [V+q]
+  double* d_tmp = nullptr;       // staging for get/set (max var size / trace chunk)
+  size_t tmp_doubles = 0;
+};
+
+template <typename T>
+static int dalloc(bnr_handle* h, T** ptr, size_t count, bool zero = true) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, count * sizeof(T) + 16));
+  if (zero) CK(cudaMemsetAsync(p, 0, count * sizeof(T) + 16, h->stream));
+  h->allocs.push_back(p);
+  *ptr = (T*)p;
+  return 0;
+}
+#define DA(ptr, count)                          \
+  do {                                          \
+    int _r = dalloc(h, &(ptr), (count));        \
+    if (_r) return _r;                          \
+  } while (0)
+
+extern "C" int bnr_version(void) { return BNR_VERSION; }
+extern "C" const char* bnr_last_error(void) { return g_err.c_str(); }
+
+extern "C" void bnr_default_params(bnr_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->num_chains = 2;
+  p->eta = 1.01; p->zeta = 1.0; p->iota = 1.0; p->a_delta = 1.0; p->b_delta = 1.0; p->nu = 10.0;
+  p->trace_full_chains = 1; p->trace_gamma_xi_all = 1; p->gig_inject_len = 64;
+}
+
+static int var_size(const Dims& d, int var) {
+  switch (var) {
+    case BNR_VAR_TAU2: case BNR_VAR_THETA: case BNR_VAR_DELTA: case BNR_VAR_MU: return 1;
+    case BNR_VAR_U: return d.R * d.V;
+    case BNR_VAR_XI: return d.V;
+    case BNR_VAR_GAMMA: case BNR_VAR_S: return d.q;
+    case BNR_VAR_M: return d.R * d.R;
+    case BNR_VAR_LAMBDA: return d.R;
+    case BNR_VAR_PI: return 3 * d.R;
+  }
+  return -1;
+}
+// offset of a variable inside a full trace row (k_record / state_elem order)
+static int row_offset(const Dims& d, int var) {
+  const int R = d.R, V = d.V, q = d.q;
+  const int o[BNR_NUM_VARS] = {0, 1, 1 + V * R, 1 + V * R + V, 1 + V * R + V + q, 1 + V * R + V + 2 * q,
+                               2 + V * R + V + 2 * q, 3 + V * R + V + 2 * q, 3 + V * R + V + 2 * q + R * R,
+                               4 + V * R + V + 2 * q + R * R, 4 + V * R + V + 2 * q + R * R + R};
+  return o[var];
+}
+
+extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y, bnr_handle** out) {
+  if (!p || !X || !y || !out) return fail(BNR_EINVAL, "null argument");
+  if (p->n < 1 || p->V < 2 || p->R < 1 || p->R > BNR_MAX_R || p->num_chains < 1)
+    return fail(BNR_EINVAL, "need n >= 1, V >= 2, 1 <= R <= 16, num_chains >= 1");
+  if (!(p->nu > p->R - 1)) return fail(BNR_EINVAL, "nu must exceed R - 1 (InverseWishart degrees of freedom)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(BNR_ENODEV, "no CUDA device visible: libbnr has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return fail(BNR_EINVAL, "device ordinal out of range");
+  CK(cudaSetDevice(p->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major < 10) return fail(BNR_ENODEV, "libbnr is built for sm_100a (B200) only");
+
+  bnr_handle* h = new bnr_handle();
+  h->p = *p;
+  if (h->p.gig_inject_len <= 0) h->p.gig_inject_len = 64;
+  Dims& d = h->e.d;
+  d.n = p->n; d.V = p->V; d.R = p->R; d.C = p->num_chains;
+  d.q = p->V * (p->V + 1) / 2;
+  d.np = (p->n + TILE_N - 1) / TILE_N * TILE_N;
+  d.qp = (d.q + TILE_K - 1) / TILE_K * TILE_K;
+  d.nparts = (d.q + PART_BLOCK - 1) / PART_BLOCK;
+  d.chain_offset = p->chain_offset;
+  d.gigK = h->p.gig_inject_len;
+  d.seed = p->seed;
+  d.eta = p->eta; d.zeta = p->zeta; d.iota = p->iota; d.a_delta = p->a_delta; d.b_delta = p->b_delta; d.nu = p->nu;
+  // dynamic shared memory of the per-chain kernels grows with V*R
+  const size_t need = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + 4 * (2 * d.V + 2 * d.R * d.R + 3 * d.R));
+  if (need > 200 * 1024 || sizeof(double) * ((size_t)d.np + 64 * 65) > 96 * 1024) {
+    delete h;
+    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R or n)");
+  }
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  linalg_setup();
+
+  Engine& e = h->e;
+  const size_t C = d.C;
+  double *dX, *dy;
+  DA(dX, (size_t)d.qp * d.np);
+  DA(dy, (size_t)d.np);
+  // X: column-major n x q host -> padded columns of np rows
+  CK(cudaMemcpy2DAsync(dX, (size_t)d.np * sizeof(double), X, (size_t)d.n * sizeof(double),
+                       (size_t)d.n * sizeof(double), (size_t)d.q, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dy, y, (size_t)d.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  e.X = dX; e.y = dy;
+  std::vector<int2> lk(d.q);
+  {
+    int j = 0;
+    for (int k = 0; k < d.V; ++k)
+      for (int l = k; l < d.V; ++l) lk[j++] = make_int2(l, k);
+  }
+  int2* dlk;
+  DA(dlk, (size_t)d.q);
+  CK(cudaMemcpyAsync(dlk, lk.data(), sizeof(int2) * d.q, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  e.edge_lk = dlk;
+
+  DA(e.tau2, C); DA(e.u, C * d.V * d.R); DA(e.u_alt, C * d.V * d.R); DA(e.xi, C * d.V);
+  DA(e.gamma, C * d.qp); DA(e.S, C * d.qp); DA(e.theta, C); DA(e.Delta, C); DA(e.M, C * d.R * d.R);
+  DA(e.mu, C); DA(e.lambda, C * d.R); DA(e.pi, C * 3 * d.R);
+  DA(e.W, C * d.qp); DA(e.v, C * d.qp); DA(e.t, C * d.qp);
+  DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
+  DA(e.G, C * d.np * d.np + 2048);
+  DA(e.partials, C * d.nparts * (2 * MAX_R + 1));
+  DA(e.status, C);
+  DA(e.iter, 1); DA(e.trace_row, 1);
+  DA(e.moments, C * 2 * (d.V + d.q) * 2);
+  DA(e.mom_window, 2);
+  DA(h->ws, x_times_workspace_doubles(d));
+  DA(h->d_rhat, (size_t)(d.V + d.q));
+  e.trace_full_chains = p->trace_rows > 0 ? (p->trace_full_chains < d.C ? p->trace_full_chains : d.C) : 0;
+  if (e.trace_full_chains < 0) e.trace_full_chains = 0;
+  e.trace_gx_all = (p->trace_rows > 0 && p->trace_gamma_xi_all) ? 1 : 0;
+  e.trace_rows = p->trace_rows > 0 ? p->trace_rows : 0;
+  e.rowlen_full = 4 + d.V * d.R + d.V + 2 * d.q + d.R * d.R + d.R + 3 * d.R;
+  e.tr_full = nullptr; e.tr_gx = nullptr;
+  if (e.trace_full_chains > 0) {
+    int r = dalloc(h, &e.tr_full, (size_t)e.trace_full_chains * e.trace_rows * e.rowlen_full, false);
+    if (r) return r;
+  }
+  if (e.trace_gx_all) {
+    int r = dalloc(h, &e.tr_gx, C * e.trace_rows * (d.V + d.q), false);
+    if (r) return r;
+  }
+  h->tmp_doubles = (size_t)1 << 22;
+  DA(h->d_tmp, h->tmp_doubles);
+  e.inj = nullptr; e.inj_stride = 0;
+  memset(&e.aux, 0, sizeof(e.aux));
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return BNR_OK;
+}
+
+extern "C" int bnr_destroy(bnr_handle* h) {
+  if (!h) return BNR_OK;
+  cudaSetDevice(h->p.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return BNR_OK;
+}
+
+static void drop_graph(bnr_handle* h) {
+  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+}
+
+// X * gamma for the current state (cache used by tau2 and mu)
+static void refresh_xg(bnr_handle* h) {
+  launch_x_times(h->e, 0, h->e.gamma, h->e.xg, h->ws, h->stream);
+  h->xg_valid = true;
+}
+
+// the gamma conditional: W, v, X v, rhs, G, Cholesky, solves, X' a4, gamma (and optionally S + lambda statistics)
+static void run_gamma(bnr_handle* h, int gig_flags) {
+  Engine& e = h->e;
+  cudaStream_t s = h->stream;
+  launch_edge_prep(e, 1, s);
+  launch_x_times(e, 0, e.v, e.xv, h->ws, s);
+  launch_rhs(e, s);
+  launch_syrk_G(e, s);
+  launch_cholesky(e, s);
+  launch_chol_solve(e, s);
+  launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
+  launch_gamma_gig(e, gig_flags, s);
+}
+
+// one full sweep in gibbs_sample! order (src/gibbs.jl:663-677)
+static void enqueue_sweep(bnr_handle* h) {
+  Engine& e = h->e;
+  cudaStream_t s = h->stream;
+  launch_tau2(e, s);
+  launch_uxi(e, s);
+  std::swap(e.u, e.u_alt);          // u now holds the new draw (pointer swap is baked per captured sweep)
+  run_gamma(h, 3);
+  launch_x_times(e, 0, e.gamma, e.xg, h->ws, s);
+  launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
+                       (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
+  launch_record(e, 1, s);
+  launch_advance(e, 1, s);
+}
+
+// The u double buffer flips every sweep, so the graph holds TWO sweeps; odd counts run one sweep eagerly.
+static int build_graph(bnr_handle* h) {
+  if (h->gexec) return BNR_OK;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  enqueue_sweep(h);
+  enqueue_sweep(h);
+  CK(cudaStreamEndCapture(h->stream, &h->graph));
+  CK(cudaGraphInstantiate(&h->gexec, h->graph, 0));
+  return BNR_OK;
+}
+
+extern "C" int bnr_init_state(bnr_handle* h) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
+  Engine& e = h->e;
+  CK(cudaMemsetAsync(e.iter, 0, sizeof(long long), h->stream));
+  CK(cudaMemsetAsync(e.trace_row, 0, sizeof(long long), h->stream));
+  CK(cudaMemsetAsync(e.status, 0, sizeof(int) * e.d.C, h->stream));
+  launch_init(e, h->stream);
+  launch_record(e, 0, h->stream);
+  launch_advance(e, 0, h->stream);
+  h->xg_valid = false;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
+  if (!h || n_iters < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (!h->xg_valid) refresh_xg(h);
+  int64_t left = n_iters;
+  if (h->e.inj == nullptr && !h->aux_on && left >= 2) {
+    int r = build_graph(h);
+    if (r) return r;
+    for (; left >= 2; left -= 2) CK(cudaGraphLaunch(h->gexec, h->stream));
+  }
+  for (; left > 0; --left) {
+    drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graph
+    enqueue_sweep(h);
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  h->ran = true;
+  return BNR_OK;
+}
+
+extern "C" int bnr_sync(bnr_handle* h) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return BNR_OK;
+}
+
+extern "C" int bnr_last_run_ms(bnr_handle* h, float* ms) {
+  if (!h || !ms || !h->ran) return fail(BNR_ESTATE, "no run recorded");
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BNR_OK;
+}
+
+extern "C" int bnr_iteration(bnr_handle* h, int64_t* completed) {
+  if (!h || !completed) return fail(BNR_EINVAL, "null argument");
+  long long v = 0;
+  CK(cudaMemcpyAsync(&v, h->e.iter, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *completed = v;
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_trace_row(bnr_handle* h, int64_t row) {
+  if (!h || row < 0) return fail(BNR_EINVAL, "bad arguments");
+  long long v = row;
+  CK(cudaMemcpyAsync(h->e.trace_row, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+extern "C" int bnr_get_trace_row(bnr_handle* h, int64_t* row) {
+  if (!h || !row) return fail(BNR_EINVAL, "null argument");
+  long long v = 0;
+  CK(cudaMemcpyAsync(&v, h->e.trace_row, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *row = v;
+  return BNR_OK;
+}
+
+extern "C" int bnr_copy_trace_rows(bnr_handle* h, int64_t dst, int64_t src, int64_t count) {
+  if (!h || dst < 0 || src < 0 || count < 0) return fail(BNR_EINVAL, "bad arguments");
+  Engine& e = h->e;
+  if (dst + count > e.trace_rows || src + count > e.trace_rows) return fail(BNR_EINVAL, "rows out of range");
+  if (count == 0 || dst == src) return BNR_OK;
+  // rows are contiguous per chain; regions may overlap -> stage through a temporary when they do
+  auto move = [&](double* base, size_t rowlen, int chains) -> int {
+    for (int c = 0; c < chains; ++c) {
+      double* b = base + (size_t)c * e.trace_rows * rowlen;
+      const size_t bytes = (size_t)count * rowlen * sizeof(double);
+      const bool overlap = !(dst + count <= src || src + count <= dst);
+      if (!overlap) {
+        CK(cudaMemcpyAsync(b + (size_t)dst * rowlen, b + (size_t)src * rowlen, bytes, cudaMemcpyDeviceToDevice, h->stream));
+      } else {
+        void* tmp = nullptr;
+        CK(cudaMalloc(&tmp, bytes));
+        CK(cudaMemcpyAsync(tmp, b + (size_t)src * rowlen, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(b + (size_t)dst * rowlen, tmp, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaFree(tmp));
+      }
+    }
+    return 0;
+  };
+  if (e.tr_full) { int r = move(e.tr_full, e.rowlen_full, e.trace_full_chains); if (r) return r; }
+  if (e.tr_gx) { int r = move(e.tr_gx, e.d.V + e.d.q, e.d.C); if (r) return r; }
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_moment_window(bnr_handle* h, int64_t first, int64_t len) {
+  if (!h || len < 0) return fail(BNR_EINVAL, "bad arguments");
+  long long w[2] = {first, len};
+  CK(cudaMemcpyAsync(h->e.mom_window, w, sizeof(w), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->mom_half = len / 2;
+  return BNR_OK;
+}
+
+extern "C" int bnr_moments_device(bnr_handle* h, double** dev_ptr, int64_t* count) {
+  if (!h || !dev_ptr || !count) return fail(BNR_EINVAL, "null argument");
+  CK(cudaStreamSynchronize(h->stream));
+  *dev_ptr = h->e.moments;
+  *count = (int64_t)h->e.d.C * 2 * (h->e.d.V + h->e.d.q) * 2;
+  return BNR_OK;
+}
+
+extern "C" int bnr_rhat_from_moments(int device, const double* dev_moments, int32_t total_chains, int32_t V,
+                                     int32_t q, int64_t half_len, double* rhat_xi, double* rhat_gamma) {
+  if (!dev_moments || total_chains < 1 || half_len < 2) return fail(BNR_EINVAL, "bad arguments (need half_len >= 2)");
+  CK(cudaSetDevice(device));
+  double* d_out = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * (V + q)));
+  launch_rhat(dev_moments, total_chains, V + q, half_len, d_out, 0);
+  std::vector<double> host(V + q);
+  cudaError_t err = cudaMemcpy(host.data(), d_out, sizeof(double) * (V + q), cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  CK(err);
+  if (rhat_xi) memcpy(rhat_xi, host.data(), sizeof(double) * V);
+  if (rhat_gamma) memcpy(rhat_gamma, host.data() + V, sizeof(double) * q);
+  return BNR_OK;
+}
+
+// two-pass split-half moments of rows [first_row, first_row + nrows) of the gamma/xi traces (what
+// return_psrf_VOI + rhat see, src/gibbs.jl:771-789).  grid = (ceil((V+q)/128), C, 2)
+__global__ void k_moments_from_trace(const double* __restrict__ tr, long long trace_rows, int nparam, long long first,
+                                     long long nrows, double* __restrict__ mom) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nparam) return;
+  const int c = blockIdx.y, half = blockIdx.z;
+  const long long h = nrows / 2;
+  const long long r0 = first + (half == 0 ? 0 : nrows - h);
+  const double* base = tr + ((size_t)c * trace_rows + r0) * nparam + p;
+  double s = 0.0;
+  for (long long r = 0; r < h; ++r) s += base[(size_t)r * nparam];
+  const double mean = s / (double)h;
+  double m2 = 0.0;
+  for (long long r = 0; r < h; ++r) { const double dl = base[(size_t)r * nparam] - mean; m2 += dl * dl; }
+  double* m = mom + (((size_t)c * 2 + half) * nparam + p) * 2;
+  m[0] = mean; m[1] = m2;
+}
+
+extern "C" int bnr_moments_from_trace(bnr_handle* h, int64_t first_row, int64_t nrows) {
+  if (!h || first_row < 0 || nrows < 0) return fail(BNR_EINVAL, "bad arguments");
+  Engine& e = h->e;
+  if (!e.tr_gx) return fail(BNR_ESTATE, "gamma/xi traces are not recorded (trace_gamma_xi_all = 0)");
+  if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
+  if (nrows / 2 < 2) return fail(BNR_EINVAL, "need at least 4 rows");
+  const int np_ = e.d.V + e.d.q;
+  dim3 grid((np_ + 127) / 128, e.d.C, 2);
+  k_moments_from_trace<<<grid, 128, 0, h->stream>>>(e.tr_gx, e.trace_rows, np_, first_row, nrows, e.moments);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->mom_half = nrows / 2;
+  return BNR_OK;
+}
+
+extern "C" int bnr_moment_half_len(bnr_handle* h, int64_t* half_len) {
+  if (!h || !half_len) return fail(BNR_EINVAL, "null argument");
+  *half_len = h->mom_half;
+  return BNR_OK;
+}
+
+extern "C" int bnr_rhat(bnr_handle* h, double* rhat_xi, double* rhat_gamma) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  if (h->mom_half < 2) return fail(BNR_ESTATE, "moment window too short for R-hat");
+  const Dims& d = h->e.d;
+  launch_rhat(h->e.moments, d.C, d.V + d.q, h->mom_half, h->d_rhat, h->stream);
+  std::vector<double> host(d.V + d.q);
+  CK(cudaMemcpyAsync(host.data(), h->d_rhat, sizeof(double) * (d.V + d.q), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (rhat_xi) memcpy(rhat_xi, host.data(), sizeof(double) * d.V);
+  if (rhat_gamma) memcpy(rhat_gamma, host.data() + d.V, sizeof(double) * d.q);
+  return BNR_OK;
+}
+
+extern "C" int bnr_var_size(bnr_handle* h, int32_t var, int64_t* n) {
+  if (!h || !n || var < 0 || var >= BNR_NUM_VARS) return fail(BNR_EINVAL, "bad arguments");
+  *n = var_size(h->e.d, var);
+  return BNR_OK;
+}
+
+static double* var_ptr(Engine& e, int c, int var) {
+  const Dims& d = e.d;
+  switch (var) {
+    case BNR_VAR_TAU2: return e.tau2 + c;
+    case BNR_VAR_U: return e.u + (size_t)c * d.V * d.R;
+    case BNR_VAR_XI: return e.xi + (size_t)c * d.V;
+    case BNR_VAR_GAMMA: return e.gamma + (size_t)c * d.qp;
+    case BNR_VAR_S: return e.S + (size_t)c * d.qp;
+    case BNR_VAR_THETA: return e.theta + c;
+    case BNR_VAR_DELTA: return e.Delta + c;
+    case BNR_VAR_M: return e.M + (size_t)c * d.R * d.R;
+    case BNR_VAR_MU: return e.mu + c;
+    case BNR_VAR_LAMBDA: return e.lambda + (size_t)c * d.R;
+    case BNR_VAR_PI: return e.pi + (size_t)c * 3 * d.R;
+  }
+  return nullptr;
+}
+
+extern "C" int bnr_get_state(bnr_handle* h, int32_t chain, int32_t var, double* out) {
+  if (!h || !out || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS)
+    return fail(BNR_EINVAL, "bad arguments");
+  const int n = var_size(h->e.d, var), R = h->e.d.R;
+  std::vector<double> tmp(n);
+  CK(cudaMemcpyAsync(tmp.data(), var_ptr(h->e, chain, var), sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (var == BNR_VAR_PI) {
+    for (int r = 0; r < R; ++r)
+      for (int c = 0; c < 3; ++c) out[r + R * c] = tmp[3 * r + c];
+  } else {
+    memcpy(out, tmp.data(), sizeof(double) * n);
+  }
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_state(bnr_handle* h, int32_t chain, int32_t var, const double* in) {
+  if (!h || !in || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS)
+    return fail(BNR_EINVAL, "bad arguments");
+  const int n = var_size(h->e.d, var), R = h->e.d.R;
+  std::vector<double> tmp(in, in + n);
+  if (var == BNR_VAR_PI)
+    for (int r = 0; r < R; ++r)
+      for (int c = 0; c < 3; ++c) tmp[3 * r + c] = in[r + R * c];
+  CK(cudaMemcpyAsync(var_ptr(h->e, chain, var), tmp.data(), sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (var == BNR_VAR_GAMMA) h->xg_valid = false;
+  return BNR_OK;
+}
+
+// gather rows [first,last) of one variable into iteration-fastest order
+__global__ void k_gather_trace(const double* __restrict__ rows, size_t rowlen, int off, int nelem, long long first,
+                               long long count, int pi_R, double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count * nelem) return;
+  const long long it = idx % count;
+  const int el = (int)(idx / count);
+  int src = el;
+  if (pi_R > 0) { const int r = el % pi_R, c = el / pi_R; src = 3 * r + c; }   // out is (R,3) column-major
+  out[idx] = rows[(size_t)(first + it) * rowlen + off + src];
+}
+
+extern "C" int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t first, int64_t last, double* out) {
+  if (!h || !out || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS || first < 0 || last < first)
+    return fail(BNR_EINVAL, "bad arguments");
+  Engine& e = h->e;
+  if (last > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
+  const Dims& d = e.d;
+  const double* rows = nullptr;
+  size_t rowlen = 0;
+  int off = 0;
+  if (chain < e.trace_full_chains && e.tr_full) {
+    rowlen = e.rowlen_full;
+    rows = e.tr_full + (size_t)chain * e.trace_rows * rowlen;
+    off = row_offset(d, var);
+  } else if (e.tr_gx && (var == BNR_VAR_XI || var == BNR_VAR_GAMMA)) {
+    rowlen = d.V + d.q;
+    rows = e.tr_gx + (size_t)chain * e.trace_rows * rowlen;
+    off = var == BNR_VAR_XI ? 0 : d.V;
+  } else {
+    return fail(BNR_ESTATE, "this variable of this chain is not traced (see trace_full_chains / trace_gamma_xi_all)");
+  }
+  const int nelem = var_size(d, var);
+  const long long count = last - first;
+  if (count == 0) return BNR_OK;
+  // chunk over elements so the staging buffer suffices
+  const long long el_per_chunk = (long long)(h->tmp_doubles / (size_t)count);
+  if (el_per_chunk < 1) return fail(BNR_EINVAL, "row range too long for the staging buffer; fetch fewer rows per call");
+  for (int e0 = 0; e0 < nelem; e0 += (int)el_per_chunk) {
+    const int ne = (int)((nelem - e0) < el_per_chunk ? (nelem - e0) : el_per_chunk);
+    const long long tot = count * ne;
+    if (var == BNR_VAR_PI) {
+      if (ne != nelem) return fail(BNR_EINVAL, "row range too long for pi");
+      k_gather_trace<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(rows, rowlen, off, ne, first, count, d.R, h->d_tmp);
+    } else {
+      k_gather_trace<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(rows, rowlen, off + e0, ne, first, count, 0, h->d_tmp);
+    }
+    CK(cudaMemcpyAsync(out + (size_t)e0 * count, h->d_tmp, sizeof(double) * tot, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return BNR_OK;
+}
+
+extern "C" int bnr_status(bnr_handle* h, int32_t* status) {
+  if (!h || !status) return fail(BNR_EINVAL, "null argument");
+  CK(cudaMemcpyAsync(status, h->e.status, sizeof(int) * h->e.d.C, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// parity-test hooks
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int bnr_injection_size(bnr_handle* h, int32_t for_init, int64_t* per_chain) {
+  if (!h || !per_chain) return fail(BNR_EINVAL, "null argument");
+  const Dims& d = h->e.d;
+  *per_chain = for_init ? InitLayout::make(d.V, d.R).total : InjLayout::make(d.n, d.V, d.R, d.gigK).total;
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_chain) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graph(h);
+  if (!inj) { h->e.inj = nullptr; h->e.inj_stride = 0; return BNR_OK; }
+  const size_t total = (size_t)per_chain * h->e.d.C;
+  if ((long long)total > h->inj_len) {
+    double* p = nullptr;
+    CK(cudaMalloc((void**)&p, total * sizeof(double)));
+    h->allocs.push_back(p);
+    h->d_inj = p;
+    h->inj_len = (long long)total;
+  }
+  CK(cudaMemcpy(h->d_inj, inj, total * sizeof(double), cudaMemcpyHostToDevice));
+  h->e.inj = h->d_inj;
+  h->e.inj_stride = per_chain;
+  return BNR_OK;
+}
+
+extern "C" int bnr_enable_aux(bnr_handle* h, int32_t on) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  const size_t C = d.C;
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graph(h);
+  if (!on) {
+    if (h->aux_on) { h->aux_saved = e.aux; memset(&e.aux, 0, sizeof(e.aux)); }
+    h->aux_on = false;
+    return BNR_OK;
+  }
+  if (h->aux_on) return BNR_OK;
+  if (h->aux_saved.tau2_params) {
+    e.aux = h->aux_saved;
+  } else {
+    DA(e.aux.tau2_params, C * 2); DA(e.aux.sigma_inv, C * d.V * d.R * d.R); DA(e.aux.sigma_chol, C * d.V * d.R * d.R);
+    DA(e.aux.mu_t, C * d.V * d.R); DA(e.aux.log_odds, C * d.V); DA(e.aux.chi, C * d.qp);
+    DA(e.aux.theta_params, C * 2); DA(e.aux.delta_params, C * 2); DA(e.aux.m_params, C * (1 + 2 * d.R * d.R));
+    DA(e.aux.mu_params, C * 2); DA(e.aux.lambda_logw, C * 3 * d.R); DA(e.aux.lambda_w, C * 3 * d.R);
+    DA(e.aux.pi_alpha, C * 3 * d.R); DA(e.aux.gig_used, C * d.qp); DA(e.aux.G_copy, C * d.np * d.np);
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  h->aux_on = true;
+  return BNR_OK;
+}
+
+extern "C" int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double* out, int64_t capacity) {
+  if (!h || !out || chain < 0 || chain >= h->e.d.C) return fail(BNR_EINVAL, "bad arguments");
+  if (!h->aux_on) return fail(BNR_ESTATE, "call bnr_enable_aux first");
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  const int R = d.R, V = d.V, RR = R * R;
+  const double* src = nullptr;
+  size_t n = 0;
+  std::vector<double> tmp;
+  switch (aux_id) {
+    case BNR_AUX_TAU2_PARAMS: src = e.aux.tau2_params + 2 * chain; n = 2; break;
+    case BNR_AUX_SIGMA_INV: src = e.aux.sigma_inv + (size_t)chain * V * RR; n = (size_t)V * RR; break;
+    case BNR_AUX_SIGMA_CHOL: src = e.aux.sigma_chol + (size_t)chain * V * RR; n = (size_t)V * RR; break;
+    case BNR_AUX_MU_T: src = e.aux.mu_t + (size_t)chain * V * R; n = (size_t)V * R; break;
+    case BNR_AUX_LOG_ODDS: src = e.aux.log_odds + (size_t)chain * V; n = V; break;
+    case BNR_AUX_W: src = e.W + (size_t)chain * d.qp; n = d.q; break;
+    case BNR_AUX_RHS: case BNR_AUX_A4: src = e.rhs + (size_t)chain * d.np; n = d.n; break;
+    case BNR_AUX_CHI: src = e.aux.chi + (size_t)chain * d.qp; n = d.q; break;
+    case BNR_AUX_THETA_PARAMS: src = e.aux.theta_params + 2 * chain; n = 2; break;
+    case BNR_AUX_DELTA_PARAMS: src = e.aux.delta_params + 2 * chain; n = 2; break;
+    case BNR_AUX_M_PARAMS: src = e.aux.m_params + (size_t)chain * (1 + 2 * RR); n = 1 + 2 * RR; break;
+    case BNR_AUX_MU_PARAMS: src = e.aux.mu_params + 2 * chain; n = 2; break;
+    case BNR_AUX_LAMBDA_LOGW: src = e.aux.lambda_logw + (size_t)chain * 3 * R; n = 3 * R; break;
+    case BNR_AUX_LAMBDA_WEIGHTS: src = e.aux.lambda_w + (size_t)chain * 3 * R; n = 3 * R; break;
+    case BNR_AUX_PI_ALPHA: src = e.aux.pi_alpha + (size_t)chain * 3 * R; n = 3 * R; break;
+    case BNR_AUX_GIG_USED: src = e.aux.gig_used + (size_t)chain * d.qp; n = d.q; break;
+    case BNR_AUX_G: case BNR_AUX_G_CHOL: {
+      // n x n sub-block of the padded np x np matrix
+      const double* base = (aux_id == BNR_AUX_G ? e.aux.G_copy : e.G) + (size_t)chain * d.np * d.np;
+      if (capacity < (int64_t)d.n * d.n) return fail(BNR_EINVAL, "capacity too small");
+      tmp.resize((size_t)d.np * d.np);
+      CK(cudaMemcpyAsync(tmp.data(), base, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      for (int j = 0; j < d.n; ++j)
+        for (int i = 0; i < d.n; ++i) {
+          double v = tmp[(size_t)j * d.np + i];
+          if (aux_id == BNR_AUX_G_CHOL && i < j) v = 0.0;
+          out[(size_t)j * d.n + i] = v;
+        }
+      return BNR_OK;
+    }
+    default: return fail(BNR_EINVAL, "unknown aux id");
+  }
+  if ((int64_t)n > capacity) return fail(BNR_EINVAL, "capacity too small");
+  CK(cudaMemcpyAsync(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+// One conditional, in place, on the state as it stands (the reference's update_*!(state, i, ...) with rows
+// i-1 / i merged: every variable holds its most recent value).
+extern "C" int bnr_step(bnr_handle* h, int32_t cond) {
+  if (!h || cond < 0 || cond >= BNR_NUM_CONDS) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
+  drop_graph(h);
+  Engine& e = h->e;
+  cudaStream_t s = h->stream;
+  switch (cond) {
+    case BNR_COND_TAU2:
+      refresh_xg(h);
+      launch_tau2(e, s);
+      break;
+    case BNR_COND_U_XI:
+      launch_uxi(e, s);
+      std::swap(e.u, e.u_alt);
+      break;
+    case BNR_COND_GAMMA:
+      run_gamma(h, 1);
+      h->xg_valid = false;
+      break;
+    case BNR_COND_D:
+      launch_edge_prep(e, 0, s);
+      launch_gamma_gig(e, 2, s);
+      break;
+    case BNR_COND_THETA: case BNR_COND_LAMBDA:
+      launch_edge_prep(e, 0, s);
+      launch_gamma_gig(e, 0, s);       // refresh sum S and the lambda statistics from the current state
+      launch_finish(e, 1 << cond, s);
+      break;
+    case BNR_COND_MU:
+      refresh_xg(h);
+      launch_finish(e, 1 << cond, s);
+      break;
+    default:
+      launch_finish(e, 1 << cond, s);
+      break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+extern "C" int bnr_finish_sweep(bnr_handle* h) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  launch_record(h->e, 1, h->stream);
+  launch_advance(h->e, 1, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+static int rng_dump(bnr_handle* h, int chain, int64_t iteration, int site, int element, int kind, double shape,
+                    int count, double* out) {
+  if (!h || !out || count < 1 || chain < 0 || chain >= h->e.d.C) return fail(BNR_EINVAL, "bad arguments");
+  if ((size_t)count > h->tmp_doubles) return fail(BNR_EINVAL, "count too large");
+  launch_rng_dump(h->e.d, chain, iteration, site, element, kind, shape, count, h->d_tmp, h->stream);
+  CK(cudaMemcpyAsync(out, h->d_tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+extern "C" int bnr_rng_stream(bnr_handle* h, int32_t chain, int64_t iteration, int32_t site, int32_t element,
+                              int32_t kind, int32_t count, double* out) {
+  if (kind != 0 && kind != 1) return fail(BNR_EINVAL, "kind must be 0 (uniform) or 1 (normal)");
+  return rng_dump(h, chain, iteration, site, element, kind, 0.0, count, out);
+}
+
+extern "C" int bnr_rng_gamma(bnr_handle* h, int32_t chain, int64_t iteration, int32_t site, int32_t element,
+                             double shape, int32_t count, double* out) {
+  if (!(shape > 0.0)) return fail(BNR_EINVAL, "shape must be positive");
+  return rng_dump(h, chain, iteration, site, element, 2, shape, count, out);
+}

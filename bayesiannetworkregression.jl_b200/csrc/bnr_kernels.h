@@ -1,0 +1,46 @@
+// Host-callable launchers shared between the translation units of libbnr.
+#pragma once
+#include <cuda_runtime.h>
+#include "bnr_engine.cuh"
+
+// internal mirrors of include/bnr.h constants (kept in sync by a static_assert in bnr_api.cu)
+#define BNR_ST_JITTER_ 1
+#define BNR_ST_SIGMA_NOTPD_ 2
+#define BNR_ST_G_NOTPD_ 4
+#define BNR_ST_GIG_CAP_ 8
+#define BNR_ST_INJ_EXHAUSTED_ 16
+#define BNR_ST_NAN_ 32
+#define BNR_ST_PSI_NOTPD_ 64
+#define BNR_COND_THETA_ 4
+#define BNR_COND_DELTA_ 5
+#define BNR_COND_M_ 6
+#define BNR_COND_MU_ 7
+#define BNR_COND_LAMBDA_ 8
+#define BNR_COND_PI_ 9
+
+namespace bnr {
+
+void launch_tau2(const Engine& e, cudaStream_t s);
+void launch_uxi(const Engine& e, cudaStream_t s);
+void launch_edge_prep(const Engine& e, int draw_v, cudaStream_t s);
+void launch_rhs(const Engine& e, cudaStream_t s);
+void launch_gamma_gig(const Engine& e, int flags, cudaStream_t s);
+void launch_finish(const Engine& e, int mask, cudaStream_t s);
+void launch_init(const Engine& e, cudaStream_t s);
+void launch_record(const Engine& e, int sweep_done, cudaStream_t s);
+void launch_advance(const Engine& e, int inc_iter, cudaStream_t s);
+void launch_rhat(const double* mom, int chains, int nparams, long long h, double* out, cudaStream_t s);
+void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, int element, int kind, double shape,
+                     int count, double* out, cudaStream_t s);
+
+// dense linear algebra (bnr_linalg.cu)
+// out[c][m] = sum_k A(m,k) v[c][k];  trans=0: A = X (np x qp), out = e.xv-like [C][np], in [C][qp]
+//                                     trans=1: A = X' (qp x np), out [C][qp], in [C][np]
+void launch_x_times(const Engine& e, int trans, const double* in, double* out, double* splitk_ws, cudaStream_t s);
+size_t x_times_workspace_doubles(const Dims& d);
+void launch_syrk_G(const Engine& e, cudaStream_t s);         // G_c = X diag(S_c) X' + I (lower tiles)
+void launch_cholesky(const Engine& e, cudaStream_t s);       // in-place lower Cholesky of every G_c
+void launch_chol_solve(const Engine& e, cudaStream_t s);     // rhs_c <- G_c^-1 rhs_c using the factor
+void linalg_setup();                                          // one-time cudaFuncSetAttribute calls
+
+}  // namespace bnr

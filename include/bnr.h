@@ -1,0 +1,194 @@
+/*
+ * libbnr -- C ABI of the B200-native Gibbs engine for Bayesian Network Regression.
+ *
+ * This is the drop-in boundary for the sampler hot path of BayesianNetworkRegression.jl:
+ *   reference interface replaced                                   entry point(s) here
+ *   -------------------------------------------------------------  ---------------------------------
+ *   initialize_and_run! / run!        src/gibbs.jl:822-846,849-864  bnr_create, bnr_init_state, bnr_run
+ *   initialize_variables!             src/gibbs.jl:191-224          bnr_init_state
+ *   gibbs_sample! + update_* (x10)    src/gibbs.jl:663-677,267-636  bnr_run (whole sweeps), bnr_step (one conditional)
+ *   sample_gig & friends              src/gig.jl:8-176              inside bnr_run / bnr_step(BNR_COND_D)
+ *   rhat / return_psrf_VOI            src/convergence.jl:4-65,
+ *                                     src/gibbs.jl:771-789          bnr_set_moment_window, bnr_rhat,
+ *                                                                   bnr_moments_device, bnr_rhat_from_moments
+ *   state Table columns (Results)     src/gibbs.jl:23-29,835-841    bnr_get_state, bnr_set_state, bnr_get_trace
+ *   pmap over chains (one process     src/gibbs.jl:946-948          num_chains batched per handle (= per GPU);
+ *   per chain)                                                      chain_offset keys the RNG by global chain id
+ *
+ * Host wrappers (Julia `ccall`, Python `ctypes`) keep everything else of Fit!/Summary: kwargs,
+ * parameters.log, setup_X!, the PSRF control loop, DataFrames.  See INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative BNR_E* code otherwise; bnr_last_error() gives
+ *    a thread-local message.  No exceptions cross the ABI.
+ *  - all host buffers are owned by the caller and never retained after the call returns;
+ *    device memory, streams and CUDA graphs are owned by the handle.
+ *  - matrices use the REFERENCE layout (Julia column-major): X is n x q with X[i + n*j];
+ *    u is R x V with u[r + R*k]; M is R x R; pi is R x 3 with pi[r + R*c], columns = P(0),P(+1),P(-1);
+ *    gamma/S have length q = V(V+1)/2 ordered as src/utils.jl:40-57 (column k, rows l = k..V, diagonal
+ *    included).  Traces are returned iteration-fastest: out[it + rows*elem], so a Julia
+ *    Array{Float64,3}(rows, d1, d2) can wrap the buffer directly.
+ *  - all arithmetic is FP64.  Random numbers: Philox4x32-10, key = (seed, global chain id),
+ *    counter = (sub-block, element, draw site, iteration): results do not depend on how chains are
+ *    distributed over handles/GPUs.
+ *  - a handle is not thread-safe.
+ */
+#ifndef BNR_H
+#define BNR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNR_VERSION 100
+
+/* error codes */
+#define BNR_OK 0
+#define BNR_EINVAL (-1)   /* bad argument */
+#define BNR_ECUDA (-2)    /* CUDA runtime error (message in bnr_last_error) */
+#define BNR_ENOMEM (-3)
+#define BNR_ESTATE (-4)   /* call not valid in the current state (e.g. trace not recorded) */
+#define BNR_ENODEV (-5)   /* no usable CUDA device: there is NO CPU fallback */
+
+/* state variables (Results.state columns, src/gibbs.jl:835-841) */
+enum {
+  BNR_VAR_TAU2 = 0, BNR_VAR_U = 1, BNR_VAR_XI = 2, BNR_VAR_GAMMA = 3, BNR_VAR_S = 4, BNR_VAR_THETA = 5,
+  BNR_VAR_DELTA = 6, BNR_VAR_M = 7, BNR_VAR_MU = 8, BNR_VAR_LAMBDA = 9, BNR_VAR_PI = 10, BNR_NUM_VARS = 11
+};
+
+/* conditionals, in gibbs_sample! order (src/gibbs.jl:666-675) */
+enum {
+  BNR_COND_TAU2 = 0, BNR_COND_U_XI = 1, BNR_COND_GAMMA = 2, BNR_COND_D = 3, BNR_COND_THETA = 4,
+  BNR_COND_DELTA = 5, BNR_COND_M = 6, BNR_COND_MU = 7, BNR_COND_LAMBDA = 8, BNR_COND_PI = 9,
+  BNR_NUM_CONDS = 10
+};
+
+/* auxiliary (intermediate) quantities exposed for level-1 parity tests; sizes in doubles per chain */
+enum {
+  BNR_AUX_TAU2_PARAMS = 0,   /* [2]        shape, scale of the InverseGamma                       */
+  BNR_AUX_SIGMA_INV = 1,     /* [V*R*R]    per node Sigma^-1 (after jitter), R x R col-major       */
+  BNR_AUX_SIGMA_CHOL = 2,    /* [V*R*R]    per node lower Cholesky factor of Sigma^-1              */
+  BNR_AUX_MU_T = 3,          /* [V*R]      per node conditional mean of u_k                        */
+  BNR_AUX_LOG_ODDS = 4,      /* [V]        log(w_bot / w_top); w = 1/(1+exp(.))                    */
+  BNR_AUX_W = 5,             /* [q]        W = lower_triangle(u' Lambda u)                         */
+  BNR_AUX_G = 6,             /* [n*n]      X D X' + I, col-major (symmetric, both triangles filled) */
+  BNR_AUX_G_CHOL = 7,        /* [n*n]      its lower Cholesky factor (strict upper = 0)            */
+  BNR_AUX_RHS = 8,           /* [n]        a1 - a3                                                  */
+  BNR_AUX_A4 = 9,            /* [n]        (X D X' + I)^-1 (a1 - a3)                                */
+  BNR_AUX_CHI = 10,          /* [q]        GIG chi_j = (gamma_j - W_j)^2 / tau2                     */
+  BNR_AUX_THETA_PARAMS = 11, /* [2]        shape, scale                                             */
+  BNR_AUX_DELTA_PARAMS = 12, /* [2]        a, b                                                     */
+  BNR_AUX_M_PARAMS = 13,     /* [1+2*R*R]  df, Psi (col-major), chol(Psi) lower                     */
+  BNR_AUX_MU_PARAMS = 14,    /* [2]        mean, sd                                                 */
+  BNR_AUX_LAMBDA_LOGW = 15,  /* [R*3]      loglik_v - max_v loglik_v, [r + R*c], c over (0,+1,-1)    */
+  BNR_AUX_LAMBDA_WEIGHTS = 16,/* [R*3]     unnormalised weights pi[r,c]*exp(logw)                   */
+  BNR_AUX_PI_ALPHA = 17,     /* [R*3]      Dirichlet parameters                                     */
+  BNR_AUX_GIG_USED = 18,     /* [q]        uniforms consumed per edge by the GIG sampler            */
+  BNR_NUM_AUX = 19
+};
+
+/* per-chain status bits (bnr_status) -- the device-side analogue of the reference's exceptions
+ * and stderr diagnostics (src/gibbs.jl:313-347, 385-402, 527-543) */
+#define BNR_ST_JITTER 1        /* Sigma^-1 needed the 1e-5 / 4e-5 jitter ladder          */
+#define BNR_ST_SIGMA_NOTPD 2   /* Sigma^-1 not PD even after the ladder (reference throws) */
+#define BNR_ST_G_NOTPD 4       /* X D X' + I lost positive definiteness                  */
+#define BNR_ST_GIG_CAP 8       /* GIG rejection loop hit the attempt cap                 */
+#define BNR_ST_INJ_EXHAUSTED 16/* injected uniform stream too short (test mode)          */
+#define BNR_ST_NAN 32          /* NaN mixture weight (reference falls back to Bernoulli(0.5)) */
+#define BNR_ST_PSI_NOTPD 64    /* I + sum u u' not PD                                    */
+
+typedef struct bnr_handle bnr_handle;
+
+typedef struct bnr_params {
+  int32_t n;                 /* samples                                                     */
+  int32_t V;                 /* nodes; q = V(V+1)/2 columns of X                            */
+  int32_t R;                 /* latent dimension, 1..BNR_MAX_R                              */
+  int32_t num_chains;        /* chains advanced in lock-step by this handle (this GPU)      */
+  int32_t chain_offset;      /* global id of local chain 0 (RNG key); 0 for single-GPU      */
+  int32_t device;            /* CUDA device ordinal                                         */
+  int32_t trace_full_chains; /* leading local chains whose FULL state is recorded per row   */
+  int32_t trace_gamma_xi_all;/* !=0: record gamma and xi rows of every chain                */
+  int64_t trace_rows;        /* capacity (rows) of the trace buffers; 0 = no traces         */
+  uint64_t seed;
+  double eta, zeta, iota, a_delta, b_delta, nu;   /* Fit! hyper-parameters (src/gibbs.jl:725) */
+  int32_t gig_inject_len;    /* K: injected uniforms per edge in injection mode (default 64) */
+  int32_t reserved;
+} bnr_params;
+
+#define BNR_MAX_R 16
+
+int bnr_version(void);
+const char* bnr_last_error(void);
+void bnr_default_params(bnr_params* p);
+
+/* X: n x q column-major host array, y: n.  Copies both to the device (padded, L2-friendly). */
+int bnr_create(const bnr_params* p, const double* X, const double* y, bnr_handle** out);
+int bnr_destroy(bnr_handle* h);
+
+/* Row 1 of every chain from the priors (initialize_variables!), iteration counter := 0. */
+int bnr_init_state(bnr_handle* h);
+
+/* Advance every chain by n_iters Gibbs sweeps (asynchronous; bnr_sync waits). */
+int bnr_run(bnr_handle* h, int64_t n_iters);
+int bnr_sync(bnr_handle* h);
+int bnr_iteration(bnr_handle* h, int64_t* completed_sweeps);
+/* milliseconds of device time of the last bnr_run (CUDA events on the handle's stream) */
+int bnr_last_run_ms(bnr_handle* h, float* ms);
+
+/* Trace row bookkeeping: the next recorded sweep is written to row `row` (0-based). Row 0 is written by
+ * bnr_init_state.  Mirrors run!'s `j` index incl. the purge_burn ring (src/gibbs.jl:851-861). */
+int bnr_set_trace_row(bnr_handle* h, int64_t row);
+int bnr_get_trace_row(bnr_handle* h, int64_t* row);
+int bnr_copy_trace_rows(bnr_handle* h, int64_t dst_row, int64_t src_row, int64_t count); /* copy_table! */
+
+/* Split-half streaming moments for R-hat: sweeps whose 1-based number s satisfies
+ * first <= s < first+len contribute; halves are [first, first+len/2) and the last len/2 sweeps. */
+int bnr_set_moment_window(bnr_handle* h, int64_t first_sweep, int64_t len);
+/* device pointer to [chain][half(2)][param(V xi then q gamma)][mean, M2] and its length in doubles */
+int bnr_moments_device(bnr_handle* h, double** dev_ptr, int64_t* count);
+/* R-hat (src/convergence.jl:4-65) from gathered moments of total_chains chains; dev_moments is a DEVICE
+ * pointer (e.g. the output of an NCCL all-gather of bnr_moments_device buffers), outputs are HOST. */
+int bnr_rhat_from_moments(int device, const double* dev_moments, int32_t total_chains, int32_t V, int32_t q,
+                          int64_t half_len, double* rhat_xi, double* rhat_gamma);
+/* fill the moments buffer from rows [first_row, first_row+nrows) of the recorded gamma/xi traces instead
+ * (exactly the rows return_psrf_VOI hands to rhat); needs trace_gamma_xi_all */
+int bnr_moments_from_trace(bnr_handle* h, int64_t first_row, int64_t nrows);
+/* draws per split chain behind the current moments buffer (len/2 of the window, or nrows/2) */
+int bnr_moment_half_len(bnr_handle* h, int64_t* half_len);
+/* convenience: R-hat over this handle's chains only */
+int bnr_rhat(bnr_handle* h, double* rhat_xi, double* rhat_gamma);
+
+/* current state of one local chain in reference layout */
+int bnr_get_state(bnr_handle* h, int32_t chain, int32_t var, double* out);
+int bnr_set_state(bnr_handle* h, int32_t chain, int32_t var, const double* in);
+int bnr_var_size(bnr_handle* h, int32_t var, int64_t* n_elems);
+/* rows [first,last) of a recorded variable, iteration-fastest: out[(it-first) + (last-first)*elem] */
+int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t first, int64_t last, double* out);
+int bnr_status(bnr_handle* h, int32_t* status_per_chain);
+
+/* ---- parity-test hooks (tests only) ---- */
+/* Injected basic variates replacing Philox: host array [num_chains][per_chain], layout documented in
+ * oracle/bnr_oracle.py:draw_layout (sweep) / init_layout (init).  NULL switches injection off. */
+int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_chain);
+int bnr_injection_size(bnr_handle* h, int32_t for_init, int64_t* per_chain);
+/* Run ONE conditional of the sweep that would produce sweep number (completed+1), in place. */
+int bnr_step(bnr_handle* h, int32_t cond);
+/* bnr_step sequence bookkeeping: call after the 10th conditional to count the sweep as completed */
+int bnr_finish_sweep(bnr_handle* h);
+int bnr_enable_aux(bnr_handle* h, int32_t on);
+int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double* out, int64_t capacity);
+/* raw basic variates of the production RNG for a draw site (lets the oracle replay Philox mode):
+ * kind 0 = uniform, 1 = normal; fills out[count] with the first `count` values of stream
+ * (iteration, site, element) of local chain `chain`. */
+int bnr_rng_stream(bnr_handle* h, int32_t chain, int64_t iteration, int32_t site, int32_t element,
+                   int32_t kind, int32_t count, double* out);
+/* unit-scale Gamma(shape) variates from the same stream machinery (Marsaglia-Tsang) */
+int bnr_rng_gamma(bnr_handle* h, int32_t chain, int64_t iteration, int32_t site, int32_t element,
+                  double shape, int32_t count, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNR_H */
