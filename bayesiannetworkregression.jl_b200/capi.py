@@ -59,6 +59,9 @@ PROTOTYPES = {
     "bnr_var_size": (C.c_int, [_H, C.c_int32, _I64P]),
     "bnr_get_trace": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _DP]),
     "bnr_status": (C.c_int, [_H, C.POINTER(C.c_int32)]),
+    "bnr_export_moments": (C.c_int, [_H, C.c_void_p]),
+    "bnr_launch_count": (C.c_int, [_H, _I64P]),
+    "bnr_profile_sweep": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "bnr_set_injection": (C.c_int, [_H, _DP, C.c_int64]),
     "bnr_injection_size": (C.c_int, [_H, C.c_int32, _I64P]),
     "bnr_step": (C.c_int, [_H, C.c_int32]),

@@ -22,6 +22,7 @@ static_assert(BNR_MAX_R == bnr::MAX_R, "MAX_R out of sync");
 using namespace bnr;
 
 static thread_local std::string g_err;
+namespace bnr { thread_local long long g_launches = 0; }
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                         \
   do {                                                                                                   \
@@ -44,7 +45,9 @@ struct bnr_handle {
   long long inj_len = 0;
   bool aux_on = false;
   Aux aux_saved = {};
-  long long mom_half = 0;        // draws per split chain behind the current moments buffer
+  long long mom_half = 0;
+  long long launches = 0;        // kernels launched by bnr_run so far (graph replays included)
+  long long graph_kernels = 0;   // kernels inside the captured two-sweep graph        // draws per split chain behind the current moments buffer
   bool xg_valid = false;         // e.xg == X * gamma for the current state
   bool ran = false;
   double* d_rhat = nullptr;      // [V+q]
@@ -251,10 +254,12 @@ static void enqueue_sweep(bnr_handle* h) {
 // The u double buffer flips every sweep, so the graph holds TWO sweeps; odd counts run one sweep eagerly.
 static int build_graph(bnr_handle* h) {
   if (h->gexec) return BNR_OK;
+  const long long before = g_launches;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   enqueue_sweep(h);
   enqueue_sweep(h);
   CK(cudaStreamEndCapture(h->stream, &h->graph));
+  h->graph_kernels = g_launches - before;
   CK(cudaGraphInstantiate(&h->gexec, h->graph, 0));
   return BNR_OK;
 }
@@ -279,16 +284,21 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
   if (!h || n_iters < 0) return fail(BNR_EINVAL, "bad arguments");
   CK(cudaSetDevice(h->p.device));
   CK(cudaEventRecord(h->ev0, h->stream));
-  if (!h->xg_valid) refresh_xg(h);
+  if (!h->xg_valid) { const long long b0 = g_launches; refresh_xg(h); h->launches += g_launches - b0; }
   int64_t left = n_iters;
   if (h->e.inj == nullptr && !h->aux_on && left >= 2) {
     int r = build_graph(h);
     if (r) return r;
-    for (; left >= 2; left -= 2) CK(cudaGraphLaunch(h->gexec, h->stream));
+    for (; left >= 2; left -= 2) {
+      CK(cudaGraphLaunch(h->gexec, h->stream));
+      h->launches += h->graph_kernels;
+    }
   }
   for (; left > 0; --left) {
     drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graph
+    const long long before = g_launches;
     enqueue_sweep(h);
+    h->launches += g_launches - before;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
@@ -744,4 +754,62 @@ extern "C" int bnr_rng_gamma(bnr_handle* h, int32_t chain, int64_t iteration, in
                              double shape, int32_t count, double* out) {
   if (!(shape > 0.0)) return fail(BNR_EINVAL, "shape must be positive");
   return rng_dump(h, chain, iteration, site, element, 2, shape, count, out);
+}
+
+extern "C" int bnr_launch_count(bnr_handle* h, int64_t* kernels) {
+  if (!h || !kernels) return fail(BNR_EINVAL, "null argument");
+  *kernels = h->launches;
+  return BNR_OK;
+}
+
+extern "C" int bnr_export_moments(bnr_handle* h, double* dev_dst) {
+  if (!h || !dev_dst) return fail(BNR_EINVAL, "null argument");
+  const size_t n = (size_t)h->e.d.C * 2 * (h->e.d.V + h->e.d.q) * 2;
+  CK(cudaMemcpyAsync(dev_dst, h->e.moments, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
+// One eager sweep with CUDA events between its phases (on the handle's stream).  ms[8]:
+// 0 tau2, 1 (u,xi), 2 gamma prep (W, v, X v, rhs), 3 SYRK X D X' + I, 4 Cholesky, 5 triangular solves,
+// 6 X' a4 + gamma + GIG, 7 X gamma + theta/Delta/M/mu/lambda/pi + record.
+extern "C" int bnr_profile_sweep(bnr_handle* h, float* ms) {
+  if (!h || !ms) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
+  drop_graph(h);
+  Engine& e = h->e;
+  cudaStream_t s = h->stream;
+  if (!h->xg_valid) refresh_xg(h);
+  cudaEvent_t ev[9];
+  for (int i = 0; i < 9; ++i) CK(cudaEventCreate(&ev[i]));
+  CK(cudaEventRecord(ev[0], s));
+  launch_tau2(e, s);
+  CK(cudaEventRecord(ev[1], s));
+  launch_uxi(e, s);
+  std::swap(e.u, e.u_alt);
+  CK(cudaEventRecord(ev[2], s));
+  launch_edge_prep(e, 1, s);
+  launch_x_times(e, 0, e.v, e.xv, h->ws, s);
+  launch_rhs(e, s);
+  CK(cudaEventRecord(ev[3], s));
+  launch_syrk_G(e, s);
+  CK(cudaEventRecord(ev[4], s));
+  launch_cholesky(e, s);
+  CK(cudaEventRecord(ev[5], s));
+  launch_chol_solve(e, s);
+  CK(cudaEventRecord(ev[6], s));
+  launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
+  launch_gamma_gig(e, 3, s);
+  CK(cudaEventRecord(ev[7], s));
+  launch_x_times(e, 0, e.gamma, e.xg, h->ws, s);
+  launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
+                       (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
+  launch_record(e, 1, s);
+  launch_advance(e, 1, s);
+  CK(cudaEventRecord(ev[8], s));
+  CK(cudaStreamSynchronize(s));
+  for (int i = 0; i < 8; ++i) CK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < 9; ++i) cudaEventDestroy(ev[i]);
+  CK(cudaGetLastError());
+  return BNR_OK;
 }

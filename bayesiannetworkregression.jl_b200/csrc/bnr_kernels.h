@@ -20,6 +20,8 @@
 
 namespace bnr {
 
+extern thread_local long long g_launches;   // kernels launched through the wrappers below (host-side count)
+
 void launch_tau2(const Engine& e, cudaStream_t s);
 void launch_uxi(const Engine& e, cudaStream_t s);
 void launch_edge_prep(const Engine& e, int draw_v, cudaStream_t s);

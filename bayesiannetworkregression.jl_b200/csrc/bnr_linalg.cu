@@ -401,7 +401,7 @@ void launch_x_times(const Engine& e, int trans, const double* in, double* out, d
   else k_x_times<0><<<grid, 256, 0, s>>>(e.X, d.np, M, K, N, in, ldin, dst, ldout, kper);
   if (ks > 1) {
     const size_t count = (size_t)N * ldout;
-    k_splitk_reduce<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(ws, out, count, ks);
+    ++g_launches; k_splitk_reduce<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(ws, out, count, ks);
   }
 }
 
@@ -416,11 +416,11 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const int T = d.np / SY_BT;
   dim3 grid(T * (T + 1) / 2, d.C);
-  k_syrk<0><<<grid, 256, SYRK_SMEM, s>>>(e.X, 0, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np,
+  ++g_launches; k_syrk<0><<<grid, 256, SYRK_SMEM, s>>>(e.X, 0, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np,
                                          d.qp / SY_BK, 0);
   if (e.aux.G_copy) {
     dim3 g2(d.np, d.C);
-    k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
+    ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
   }
 }
 
@@ -429,14 +429,14 @@ void launch_cholesky(const Engine& e, cudaStream_t s) {
   const size_t cs = (size_t)d.np * d.np;
   const int T = d.np / CHOL_NB;
   for (int kb = 0; kb < T; ++kb) {
-    k_potf2<<<d.C, 256, 0, s>>>(e.G, cs, d.np, kb, e.status);
+    ++g_launches; k_potf2<<<d.C, 256, 0, s>>>(e.G, cs, d.np, kb, e.status);
     const int rows = d.np - (kb + 1) * CHOL_NB;
     if (rows <= 0) break;
     dim3 g1((rows + 127) / 128, d.C);
-    k_trsm_panel<<<g1, 128, 0, s>>>(e.G, cs, d.np, kb);
+    ++g_launches; k_trsm_panel<<<g1, 128, 0, s>>>(e.G, cs, d.np, kb);
     const int Tt = (rows + SY_BT - 1) / SY_BT;
     dim3 g2(Tt * (Tt + 1) / 2, d.C);
-    k_syrk<1><<<g2, 256, SYRK_SMEM, s>>>(e.G + (size_t)kb * CHOL_NB * d.np, cs, d.np, nullptr, 0, e.G, cs, d.np,
+    ++g_launches; k_syrk<1><<<g2, 256, SYRK_SMEM, s>>>(e.G + (size_t)kb * CHOL_NB * d.np, cs, d.np, nullptr, 0, e.G, cs, d.np,
                                          CHOL_NB / SY_BK, (kb + 1) * CHOL_NB);
   }
 }
@@ -444,8 +444,8 @@ void launch_cholesky(const Engine& e, cudaStream_t s) {
 void launch_chol_solve(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const size_t sm = sizeof(double) * ((size_t)d.np + CHOL_NB * 65);
-  k_trsv_fwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
-  k_trsv_bwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
+  ++g_launches; k_trsv_fwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
+  ++g_launches; k_trsv_bwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
 }
 
 }  // namespace bnr

@@ -728,46 +728,46 @@ __global__ void k_rng_dump(Dims d, int chain, long long iteration, int site, int
 static size_t smem_u(const Dims& d) { return sizeof(double) * ((size_t)d.V * d.R + d.R + 64); }
 
 void launch_tau2(const Engine& e, cudaStream_t s) {
-  k_tau2<<<e.d.C, 256, smem_u(e.d), s>>>(e);
+  ++g_launches; k_tau2<<<e.d.C, 256, smem_u(e.d), s>>>(e);
 }
 void launch_uxi(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const size_t per_warp = 2 * d.V + 2 * d.R * d.R + 3 * d.R;
   const size_t sm = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + UXI_WARPS * per_warp);
   dim3 grid((d.V + UXI_WARPS - 1) / UXI_WARPS, d.C);
-  k_uxi<<<grid, 32 * UXI_WARPS, sm, s>>>(e);
+  ++g_launches; k_uxi<<<grid, 32 * UXI_WARPS, sm, s>>>(e);
 }
 void launch_edge_prep(const Engine& e, int draw_v, cudaStream_t s) {
   dim3 grid(e.d.nparts, e.d.C);
-  k_edge_prep<<<grid, PART_BLOCK, smem_u(e.d), s>>>(e, draw_v);
+  ++g_launches; k_edge_prep<<<grid, PART_BLOCK, smem_u(e.d), s>>>(e, draw_v);
 }
 void launch_rhs(const Engine& e, cudaStream_t s) {
   dim3 grid((e.d.np + 255) / 256, e.d.C);
-  k_rhs<<<grid, 256, 0, s>>>(e);
+  ++g_launches; k_rhs<<<grid, 256, 0, s>>>(e);
 }
 void launch_gamma_gig(const Engine& e, int flags, cudaStream_t s) {
   dim3 grid(e.d.nparts, e.d.C);
   const size_t sm = sizeof(double) * ((size_t)e.d.V * e.d.R + (2 * MAX_R + 1) * 8);
-  k_gamma_gig<<<grid, PART_BLOCK, sm, s>>>(e, flags);
+  ++g_launches; k_gamma_gig<<<grid, PART_BLOCK, sm, s>>>(e, flags);
 }
 void launch_finish(const Engine& e, int mask, cudaStream_t s) {
   const size_t sm = sizeof(double) * ((size_t)e.d.V * e.d.R + e.d.R * e.d.R + 2 * MAX_R + 1 + 32);
-  k_finish<<<e.d.C, 256, sm, s>>>(e, mask);
+  ++g_launches; k_finish<<<e.d.C, 256, sm, s>>>(e, mask);
 }
 void launch_init(const Engine& e, cudaStream_t s) {
-  k_init<<<e.d.C, 256, smem_u(e.d), s>>>(e);
+  ++g_launches; k_init<<<e.d.C, 256, smem_u(e.d), s>>>(e);
 }
 void launch_record(const Engine& e, int sweep_done, cudaStream_t s) {
   dim3 grid((e.d.V + e.d.q + 255) / 256, e.d.C);
-  k_record<<<grid, 256, 0, s>>>(e, sweep_done);
+  ++g_launches; k_record<<<grid, 256, 0, s>>>(e, sweep_done);
 }
 void launch_advance(const Engine& e, int inc_iter, cudaStream_t s) { k_advance<<<1, 32, 0, s>>>(e, inc_iter); }
 void launch_rhat(const double* mom, int chains, int nparams, long long h, double* out, cudaStream_t s) {
-  k_rhat<<<(nparams + 127) / 128, 128, 0, s>>>(mom, chains, nparams, h, out);
+  ++g_launches; k_rhat<<<(nparams + 127) / 128, 128, 0, s>>>(mom, chains, nparams, h, out);
 }
 void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, int element, int kind, double shape,
                      int count, double* out, cudaStream_t s) {
-  k_rng_dump<<<1, 32, 0, s>>>(d, chain, iteration, site, element, kind, shape, count, out);
+  ++g_launches; k_rng_dump<<<1, 32, 0, s>>>(d, chain, iteration, site, element, kind, shape, count, out);
 }
 
 }  // namespace bnr

@@ -133,6 +133,21 @@ class Engine:
                                             int(half_len), _dp(rx), _dp(rg)))
         return rx, rg
 
+    def export_moments(self, dev_ptr):
+        check(self._L.bnr_export_moments(self._h, C.c_void_p(dev_ptr)))
+
+    def launch_count(self):
+        v = C.c_int64()
+        check(self._L.bnr_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    PHASES = ("tau2", "u_xi", "gamma_prep", "syrk", "cholesky", "solves", "xt_gamma_gig", "xg_scalars_record")
+
+    def profile_sweep(self):
+        ms = (C.c_float * 8)()
+        check(self._L.bnr_profile_sweep(self._h, ms))
+        return dict(zip(self.PHASES, [float(x) for x in ms]))
+
     # -- state / traces in reference layout ------------------------------------------------------------
     def var_shape(self, var):
         R, V, q = self.R, self.V, self.q

@@ -168,6 +168,14 @@ int bnr_var_size(bnr_handle* h, int32_t var, int64_t* n_elems);
 int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t first, int64_t last, double* out);
 int bnr_status(bnr_handle* h, int32_t* status_per_chain);
 
+/* copy the moments buffer into caller-owned DEVICE memory (e.g. the input of an NCCL all-gather) */
+int bnr_export_moments(bnr_handle* h, double* dev_dst);
+/* number of CUDA kernels launched by bnr_run on this handle so far (graph replays counted per kernel node) */
+int bnr_launch_count(bnr_handle* h, int64_t* kernels);
+/* one eager sweep with CUDA events between phases; ms[8] = tau2, (u,xi), gamma prep, SYRK, Cholesky, solves,
+ * X'a4+gamma+GIG, X gamma + scalar conditionals + record */
+int bnr_profile_sweep(bnr_handle* h, float* ms);
+
 /* ---- parity-test hooks (tests only) ---- */
 /* Injected basic variates replacing Philox: host array [num_chains][per_chain], layout documented in
  * oracle/bnr_oracle.py:draw_layout (sweep) / init_layout (init).  NULL switches injection off. */

@@ -180,23 +180,38 @@ def test_posterior_matches_oracle_chain(bnr, golden):
 
 
 def test_posterior_vs_reference_golden(bnr, golden):
-    """The reference's own stored run (res2: 200 post-burn draws of ONE chain on test1.csv) is a noisy but real
-    Julia posterior sample: its scalar summaries must sit within 4 combined MC s.e. of the GPU sampler's."""
+    """The reference's own stored run (res2: seed 1234, ONE chain, 200 burn-in + 200 retained draws on
+    test1.csv, test/test1-generate-samples-test.jl:10-12) is a real Julia sample of this run protocol.  The GPU
+    sampler replays the same protocol on 96 independent chains; every summary of the Julia run must lie within
+    4 standard deviations of the replicate distribution (chains this short have not converged, so the replicate
+    spread -- not a within-chain s.e. -- is the honest yardstick)."""
     X, y = golden["test1.X"], golden["test1.y"]
-    nburn, nsamp, C = 600, 1000, 8
-    with bnr.Engine(X, y, 5, num_chains=C, seed=7, trace_rows=nburn + nsamp + 1, trace_full_chains=C) as eng:
+    nburn, nsamp, C = 200, 200, 96
+    with bnr.Engine(X, y, 5, num_chains=C, seed=7, trace_rows=nburn + nsamp, trace_full_chains=C,
+                    trace_gamma_xi_all=False) as eng:
         eng.init_state()
-        eng.run(nburn + nsamp)
-        gp = {k: np.concatenate([eng.get_trace(c, k, nburn + 1, nburn + nsamp + 1).reshape(nsamp, -1)
-                                 for c in range(C)]) for k in ("tau2", "mu", "theta", "Delta", "xi")}
-    ref = {k: golden["res2." + k][200:400].reshape(200, -1) for k in gp}
-    for k in ("tau2", "mu", "theta", "Delta"):
-        se = math.sqrt(_batch_se(gp[k], 20)[0] ** 2 + _batch_se(ref[k], 5)[0] ** 2)
-        assert abs(gp[k].mean() - ref[k].mean()) < 4.0 * se + 1e-12, (k, gp[k].mean(), ref[k].mean(), se)
-    # node-inclusion probability averaged over nodes
-    a, b = gp["xi"].mean(axis=1), ref["xi"].mean(axis=1)
-    se = math.sqrt(_batch_se(a, 20) ** 2 + _batch_se(b, 5) ** 2)
-    assert abs(a.mean() - b.mean()) < 4.0 * se
+        eng.run(nburn + nsamp - 1)          # rows 1..400 of the reference table = init + 399 sweeps
+        rep = {k: np.stack([eng.get_trace(c, k, nburn, nburn + nsamp).reshape(nsamp, -1) for c in range(C)])
+               for k in ("tau2", "mu", "theta", "Delta", "xi", "gamma", "S")}
+        assert not (eng.status() & ~1).any()
+    ref = {k: golden["res2." + k][nburn:nburn + nsamp].reshape(nsamp, -1) for k in rep}
+    stats_ = {
+        "mean tau2": lambda t: t["tau2"].mean(axis=-2)[..., 0],
+        "mean mu": lambda t: t["mu"].mean(axis=-2)[..., 0],
+        "mean theta": lambda t: t["theta"].mean(axis=-2)[..., 0],
+        "mean Delta": lambda t: t["Delta"].mean(axis=-2)[..., 0],
+        "mean xi": lambda t: t["xi"].mean(axis=(-2, -1)),
+        "mean |gamma|": lambda t: np.abs(t["gamma"]).mean(axis=(-2, -1)),
+        "mean log S": lambda t: np.log(t["S"]).mean(axis=(-2, -1)),
+        "sd tau2": lambda t: t["tau2"].std(axis=-2)[..., 0],
+    }
+    bad = []
+    for name, f in stats_.items():
+        r = f(rep)
+        z = (f(ref) - r.mean()) / r.std(ddof=1)
+        if abs(z) > 4.0:
+            bad.append((name, float(z), float(f(ref)), float(r.mean()), float(r.std(ddof=1))))
+    assert not bad, bad
 
 
 def test_full_size_properties(bnr):
