@@ -130,9 +130,9 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   d.eta = p->eta; d.zeta = p->zeta; d.iota = p->iota; d.a_delta = p->a_delta; d.b_delta = p->b_delta; d.nu = p->nu;
   // dynamic shared memory of the per-chain kernels grows with V*R
   const size_t need = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + 4 * (2 * d.V + 2 * d.R * d.R + 3 * d.R));
-  if (need > 200 * 1024 || sizeof(double) * ((size_t)d.np + 64 * 65) > 96 * 1024) {
+  if (need > 200 * 1024 || d.np > 1024) {
     delete h;
-    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R or n)");
+    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R, or n > 1024)");
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -167,6 +167,7 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   DA(e.W, C * d.qp); DA(e.v, C * d.qp); DA(e.t, C * d.qp);
   DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
   DA(e.G, C * d.np * d.np + 2048);
+  DA(e.dinv, C * d.np);
   DA(e.partials, C * d.nparts * (2 * MAX_R + 1));
   DA(e.status, C);
   DA(e.iter, 1); DA(e.trace_row, 1);

@@ -99,6 +99,7 @@ struct Engine {
   double* xv;       // [C][np]  X (W + delta1)
   double* rhs;      // [C][np]  a1 - a3, then L^-1 rhs, then a4 (in place)
   double* G;        // [C][np*np] col-major, lower triangle used
+  double* dinv;     // [C][np]  reciprocal diagonal of the Cholesky factor
   double* partials; // [C][nparts][2*MAX_R+1]  block partial sums: A_r, B_r (lambda), sum S
   int* status;      // [C]
   long long* iter;  // device scalar: completed sweeps

@@ -1,7 +1,7 @@
 // Dense FP64 linear algebra of the gamma draw (update_gamma!, src/gibbs.jl:420-438), batched over chains:
-//   G_c = X diag(S_c) X' + I          -> k_syrk<0>  : FP64 tensor-core (DMMA m8n8k4) SYRK, cp.async 3-stage pipeline
-//   G_c = L_c L_c'                    -> blocked right-looking Cholesky: k_potf2 / k_trsm_panel / k_syrk<1>
-//   a4  = L_c^-T L_c^-1 rhs           -> k_trsv_fwd / k_trsv_bwd
+//   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, cp.async 3-stage pipeline
+//   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_chol_update (DMMA) / k_potf2_128 / k_trsm_128
+//   a4  = L_c^-T w                    -> k_trsv_bwd128
 //   X v, X' a4 (all chains at once)   -> k_x_times (tall-skinny GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
 #include "bnr_engine.cuh"
@@ -27,7 +27,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ------------------------------------------------------------------------------------------------------------
 // SYRK on FP64 tensor cores.
 //   MODE 0:  C_c[i][j] = sum_k A[i][k] s_c[k] A[j][k] + (i==j)      A = X (shared by all chains), K = qp
-//   MODE 1:  C_c[i][j] -= sum_k P_c[i][k] P_c[j][k]                  P_c = a 64-column panel of C_c itself
+//   MODE 1:  C_c[i][j] -= sum_{k < nk*16} L_c[i][k] L_c[j][k]        left-looking Cholesky update of block column J
 // The operand is "k-major": element (row, k) at A[row + ld*k] (rows contiguous) - exactly how X (column-major
 // n x q) and a column panel of the column-major G are stored, so tiles are staged with 16-byte cp.async and no
 // transposition.  CTA tile 128 x 128, k-step 16, 8 warps (2 along j x 4 along i), warp tile 64(j) x 32(i):
@@ -43,19 +43,26 @@ constexpr int SY_STAGE_DBL = 2 * SY_BK * SY_LDS + SY_BK;   // two operand tiles 
 constexpr size_t SYRK_SMEM = (size_t)SY_STAGES * SY_STAGE_DBL * sizeof(double);
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 1)
-k_syrk(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
+__device__ __forceinline__ void
+syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
        size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nk, int origin) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.y;
-  // lower-triangular tile enumeration: t -> (ib >= jb)
-  const int t = blockIdx.x;
-  int ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
-  while (ib * (ib + 1) / 2 > t) --ib;
-  const int jb = t - ib * (ib + 1) / 2;
-  const int i0 = origin + ib * SY_BT, j0 = origin + jb * SY_BT;
+  int ib, jb;
+  if (MODE == 0) {
+    // lower-triangular tile enumeration: t -> (ib >= jb)
+    const int t = blockIdx.x;
+    ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+    while (ib * (ib + 1) / 2 > t) --ib;
+    jb = t - ib * (ib + 1) / 2;
+  } else {
+    // left-looking update of block column J = origin: tiles (J + blockIdx.x, J)
+    jb = origin;
+    ib = origin + blockIdx.x;
+  }
+  const int i0 = ib * SY_BT, j0 = jb * SY_BT;
   const double* Ac = A + (size_t)c * a_chain_stride;
   const double* sc = (MODE == 0) ? scale + (size_t)c * scale_stride : nullptr;
 
@@ -138,157 +145,291 @@ k_syrk(const double* __restrict__ A, size_t a_chain_stride, int ld, const double
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Cholesky panel kernels (NB = 64)
-// ------------------------------------------------------------------------------------------------------------
-// factor the 64 x 64 diagonal block kb of every chain in shared memory.  grid = C, block = 256.
-__global__ void __launch_bounds__(256) k_potf2(double* __restrict__ G, size_t chain_stride, int np, int kb, int* status) {
-  __shared__ double Ls[CHOL_NB][CHOL_NB + 1];
-  const int c = blockIdx.x, tid = threadIdx.x;
-  double* Gc = G + (size_t)c * chain_stride + (size_t)kb * CHOL_NB * np + (size_t)kb * CHOL_NB;
-  for (int id = tid; id < CHOL_NB * CHOL_NB; id += 256) {
-    const int r = id & 63, cc = id >> 6;
-    Ls[r][cc] = (r >= cc) ? Gc[(size_t)cc * np + r] : 0.0;
-  }
-  __syncthreads();
-  // right-looking elimination with the column scaling deferred to the write-back: one barrier per column.
-  // Ls[r][cc] -= a_rj a_ccj / d_jj only touches columns > j, so column j and d_jj are read-only in step j.
-  const int r = tid & 63, cg = tid >> 6;
-  for (int j = 0; j < CHOL_NB; ++j) {
-    __syncthreads();
-    const double djj = Ls[j][j];
-    if (tid == 0 && !(djj > 0.0)) atomicOr(&status[c], BNR_ST_G_NOTPD_);
-    const double lrj = Ls[r][j] / djj;
-    for (int cc = j + 1 + cg; cc <= r; cc += 4) Ls[r][cc] -= lrj * Ls[cc][j];
-  }
-  __syncthreads();
-  for (int id = tid; id < CHOL_NB * CHOL_NB; id += 256) {
-    const int rr = id & 63, cc = id >> 6;
-    if (rr >= cc) {
-      const double sd = sqrt(Ls[cc][cc]);
-      Gc[(size_t)cc * np + rr] = (rr == cc) ? sd : Ls[rr][cc] / sd;
-    }
-  }
+__global__ void __launch_bounds__(256, 1)
+k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ scale, size_t scale_stride,
+            double* __restrict__ G, size_t g_chain_stride, int np, int nk) {
+  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nk, 0);
 }
 
-// panel solve below the diagonal block: L21 = A21 L11^-T, one thread per row.  grid = (ceil(rows/128), C), block 128
-__global__ void __launch_bounds__(128) k_trsm_panel(double* __restrict__ G, size_t chain_stride, int np, int kb) {
-  __shared__ double Ls[CHOL_NB * CHOL_NB];   // L11 row-major: Ls[j*64 + p] = L11[j][p]
-  __shared__ double dinv[CHOL_NB];
+__global__ void __launch_bounds__(256, 1)
+k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nk,
+              int origin) {
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nk, origin);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Blocked left-looking Cholesky, block size 128, with the forward solve L w = rhs folded in.
+//   for J = 0 .. np/128-1:
+//     k_chol_update   (DMMA, above):  G[J.., J] -= L[J.., 0:J] L[J, 0:J]'
+//     k_potf2_128     one CTA per chain: rhs_J -= L[J, 0:J] w[0:J]; factor the 128 x 128 diagonal block in shared
+//                     memory (4 sub-blocks of 32: a warp factors 32 x 32 in registers with shuffles, threads eliminate
+//                     the rows below, everybody updates the trailing part in 2 x 2 register tiles); rhs_J rides along as
+//                     row 128, so w_J = L_JJ^-1 rhs_J comes out of the same elimination.  1/L_jj goes to `dinv`.
+//     k_trsm_128      rows below the diagonal block: L[i, J] = G[i, J] L_JJ^-T, one thread per row, two 64-column
+//                     halves, right-looking inside the thread (independent FMAs, no divisions).
+// All inner loops are arranged so that consecutive FP64 FMAs are independent: these kernels are latency-bound.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PB = 128;            // panel / diagonal block size
+constexpr int PB_LD = PB + 1;      // shared-memory row stride of the (PB+1) x PB working block
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)(PB + 1) * PB_LD + 1024 + 32);
+
+__global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_t chain_stride, int np, int J,
+                                                   double* __restrict__ rhs, double* __restrict__ dinv_out,
+                                                   int* status) {
+  extern __shared__ double sm[];
+  double* A = sm;                          // A[r][c] at A[r * PB_LD + c], rows 0..128 (row 128 = rhs), cols 0..127
+  double* wprev = sm + (PB + 1) * PB_LD;   // [<= 1024] previously solved w (J*128 entries used)
+  double* dinv = wprev + 1024;             // [32] reciprocal diagonal of the current 32-block
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Gc = G + (size_t)c * chain_stride;
+  double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
+  double* rc = rhs + (size_t)c * np;
+  const int kprev = J * PB;
+  for (int id = tid; id < PB * PB; id += 256) {
+    const int r = id & (PB - 1), cc = id >> 7;
+    A[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
+  }
+  for (int k = tid; k < kprev; k += 256) wprev[k] = rc[k];
+  __syncthreads();
+  // rhs_J -= L[J-block rows, 0:kprev] w[0:kprev]  (thread (jj, half) walks half of the columns; coalesced in jj)
+  {
+    const int jj = tid & (PB - 1), half = tid >> 7;
+    const double* Lrow = Gc + (size_t)J * PB + jj;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int k0 = half * (kprev / 2), k1 = half ? kprev : kprev / 2;
+    for (int k = k0; k < k1; k += 4) {      // kprev is a multiple of 128
+      a0 += Lrow[(size_t)k * np] * wprev[k];
+      a1 += Lrow[(size_t)(k + 1) * np] * wprev[k + 1];
+      a2 += Lrow[(size_t)(k + 2) * np] * wprev[k + 2];
+      a3 += Lrow[(size_t)(k + 3) * np] * wprev[k + 3];
+    }
+    const double acc = (a0 + a1) + (a2 + a3);
+    double* part = A + PB * PB_LD;          // row 128 of the working block
+    if (half == 0) part[jj] = rc[kprev + jj] - acc;
+    __syncthreads();
+    if (half == 1) part[jj] -= acc;
+  }
+  __syncthreads();
+  bool bad = false;
+  for (int s = 0; s < PB / 32; ++s) {
+    const int o = s * 32;
+    if (warp == 0) {
+      // 32 x 32 Cholesky in registers: lane r holds row o+r (columns o .. o+31)
+      double a[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = A[(o + lane) * PB_LD + o + j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double djj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(djj > 0.0)) bad = true;
+        const double inv = rsqrt(djj);
+        const double lj = (lane == j) ? djj * inv : a[j] * inv;
+        a[j] = lj;
+        if (lane == j) dinv[j] = inv;
+#pragma unroll
+        for (int cc = j + 1; cc < 32; ++cc) {
+          const double lcj = __shfl_sync(0xffffffffu, lj, cc);
+          a[cc] -= lj * lcj;                 // lanes < cc compute garbage in their (unused) upper part
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (lane >= j) A[(o + lane) * PB_LD + o + j] = a[j];
+    }
+    __syncthreads();
+    // rows below (incl. the rhs row 128): x L_ss' = a, thread per row, right-looking (independent FMAs)
+    const int nbelow = PB + 1 - (o + 32);
+    if (tid < nbelow) {
+      double* row = A + (o + 32 + tid) * PB_LD + o;
+      double x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = row[j];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double xj = x[j] * dinv[j];
+        x[j] = xj;
+#pragma unroll
+        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + k) * PB_LD + o + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) row[j] = x[j];
+    }
+    __syncthreads();
+    // trailing update inside the block in 2 x 2 register tiles:
+    //   A[r][cc] -= sum_p L[r][o+p] L[cc][o+p],  o+32 <= cc <= r <= 128 (cc < 128)
+    const int base = o + 32;
+    const int nr2 = (PB + 1 - base + 1) / 2;     // row pairs (rows base .. 128)
+    const int nc2 = (PB - base) / 2;             // column pairs (cols base .. 127), even count
+    for (int id = tid; id < nr2 * nc2; id += 256) {
+      const int r = base + 2 * (id / nc2), cc = base + 2 * (id % nc2);
+      if (cc > r + 1) continue;
+      const int r1 = (r + 1 <= PB) ? r + 1 : r;  // clamp the phantom row 129
+      const double* La = A + r * PB_LD + o;
+      const double* Lb = A + r1 * PB_LD + o;
+      const double* Lc = A + cc * PB_LD + o;
+      const double* Ld = A + (cc + 1) * PB_LD + o;
+      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+      for (int p = 0; p < 32; ++p) {
+        const double la = La[p], lb = Lb[p], lc = Lc[p], ld = Ld[p];
+        s00 += la * lc; s01 += la * ld; s10 += lb * lc; s11 += lb * ld;
+      }
+      A[r * PB_LD + cc] -= s00;
+      if (cc + 1 <= r) A[r * PB_LD + cc + 1] -= s01;
+      if (r1 != r) {
+        A[r1 * PB_LD + cc] -= s10;
+        A[r1 * PB_LD + cc + 1] -= s11;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) dinv_out[(size_t)c * np + kprev + o + tid] = dinv[tid];
+  }
+  if (bad) atomicOr(&status[c], BNR_ST_G_NOTPD_);
+  for (int id = tid; id < PB * PB; id += 256) {
+    const int r = id & (PB - 1), cc = id >> 7;
+    if (r >= cc) D[(size_t)cc * np + r] = A[r * PB_LD + cc];
+  }
+  if (tid < PB) rc[kprev + tid] = A[PB * PB_LD + tid];
+}
+
+// rows below the diagonal block.  grid = (rows_below / 128, C), block = 128.
+// shared: Lt11, Lt21, Lt22 as [p][j] (column p of the 64 x 64 sub-block contiguous in j) + 128 reciprocal diagonals
+constexpr size_t TRSM_SMEM = sizeof(double) * (3 * 64 * 64 + 128);
+
+__global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t chain_stride, int np, int J,
+                                                  const double* __restrict__ dinv_g) {
+  extern __shared__ double sm[];
+  double* L11 = sm;                 // [p][j] = L11[j][p]
+  double* L21 = sm + 64 * 64;       // [p][j] = L21[j][p]   (j: second-half column, p: first-half column)
+  double* L22 = sm + 2 * 64 * 64;
+  double* dinv = sm + 3 * 64 * 64;
   const int c = blockIdx.y, tid = threadIdx.x;
   double* Gc = G + (size_t)c * chain_stride;
-  const double* D = Gc + (size_t)kb * CHOL_NB * np + (size_t)kb * CHOL_NB;
-  for (int id = tid; id < CHOL_NB * CHOL_NB; id += 128) {
-    const int r = id & 63, cc = id >> 6;
-    Ls[r * CHOL_NB + cc] = D[(size_t)cc * np + r];
+  const double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
+  for (int id = tid; id < 64 * 64; id += 128) {
+    const int r = id & 63, cc = id >> 6;          // D(r, cc) column-major: coalesced in r
+    L11[cc * 64 + r] = D[(size_t)cc * np + r];
+    L21[cc * 64 + r] = D[(size_t)cc * np + 64 + r];
+    L22[cc * 64 + r] = D[(size_t)(64 + cc) * np + 64 + r];
   }
+  dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
   __syncthreads();
-  if (tid < CHOL_NB) dinv[tid] = 1.0 / Ls[tid * CHOL_NB + tid];
-  __syncthreads();
-  const int row = (kb + 1) * CHOL_NB + blockIdx.x * 128 + tid;
+  const int row = (J + 1) * PB + blockIdx.x * 128 + tid;
   if (row >= np) return;
-  double* prow = Gc + (size_t)kb * CHOL_NB * np + row;
-  double x[CHOL_NB];
+  double* prow = Gc + (size_t)J * PB * np + row;
+  double* prow2 = prow + (size_t)64 * np;
+  double x[64];
 #pragma unroll
-  for (int j = 0; j < CHOL_NB; ++j) x[j] = prow[(size_t)j * np];
+  for (int j = 0; j < 64; ++j) x[j] = prow[(size_t)j * np];
+  // first half: x_j = a_j / L11[j][j]; a_k -= x_j L11[k][j] (k > j)
 #pragma unroll
-  for (int j = 0; j < CHOL_NB; ++j) {
-    double s = x[j];
+  for (int j = 0; j < 64; ++j) {
+    const double xj = x[j] * dinv[j];
+    x[j] = xj;
+    const double* l1 = L11 + j * 64;
 #pragma unroll
-    for (int p = 0; p < j; ++p) s -= x[p] * Ls[j * CHOL_NB + p];
-    x[j] = s * dinv[j];
+    for (int k = j + 1; k < 64; ++k) x[k] -= xj * l1[k];
   }
 #pragma unroll
-  for (int j = 0; j < CHOL_NB; ++j) prow[(size_t)j * np] = x[j];
+  for (int j = 0; j < 64; ++j) prow[(size_t)j * np] = x[j];
+  // second half, 16 columns at a time: y_k = A[row][64 + k] - sum_p x_p L21[k][p]
+#pragma unroll 1
+  for (int k0 = 0; k0 < 64; k0 += 16) {
+    double y[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) y[k] = prow2[(size_t)(k0 + k) * np];
+#pragma unroll
+    for (int p = 0; p < 64; ++p) {
+      const double* l2 = L21 + p * 64 + k0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) y[k] -= x[p] * l2[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) prow2[(size_t)(k0 + k) * np] = y[k];
+  }
+#pragma unroll
+  for (int j = 0; j < 64; ++j) x[j] = prow2[(size_t)j * np];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const double yj = x[j] * dinv[64 + j];
+    x[j] = yj;
+    const double* l2 = L22 + j * 64;
+#pragma unroll
+    for (int k = j + 1; k < 64; ++k) x[k] -= yj * l2[k];
+  }
+#pragma unroll
+  for (int j = 0; j < 64; ++j) prow2[(size_t)j * np] = x[j];
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// triangular solves with the factor: rhs <- L^-1 rhs (fwd), rhs <- L^-T rhs (bwd).  grid = C, block = 256.
+// backward solve  L' x = w  (w in rhs, overwritten by x), left-looking over 128-blocks from the bottom.
+// grid = C, block = 256 (8 warps): warp per column group for the matvec with the rows below (coalesced, 8 columns in
+// flight per warp), then a 128 x 128 transposed triangular solve by one warp (shuffles, reciprocal diagonals).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_trsv_fwd(const double* __restrict__ G, size_t chain_stride, int np,
-                                                  double* __restrict__ rhs) {
-  extern __shared__ double sm[];
-  double* r = sm;                       // [np]
-  double* Ls = r + np;                  // [64*65]
-  const int c = blockIdx.x, tid = threadIdx.x;
-  const double* Gc = G + (size_t)c * chain_stride;
-  for (int i = tid; i < np; i += 256) r[i] = rhs[(size_t)c * np + i];
-  const int T = np / CHOL_NB;
-  for (int kb = 0; kb < T; ++kb) {
-    const double* D = Gc + (size_t)kb * CHOL_NB * np + (size_t)kb * CHOL_NB;
-    __syncthreads();
-    for (int id = tid; id < CHOL_NB * CHOL_NB; id += 256) {
-      const int rr = id & 63, cc = id >> 6;
-      Ls[rr * 65 + cc] = D[(size_t)cc * np + rr];
-    }
-    __syncthreads();
-    double* x = r + kb * CHOL_NB;
-    if (tid < 32) {   // one warp solves the 64 x 64 lower system; lane owns rows lane and lane+32
-      double x0 = x[tid], x1 = x[tid + 32];
-      for (int j = 0; j < CHOL_NB; ++j) {
-        double xj;
-        if (j < 32) { xj = __shfl_sync(0xffffffffu, x0, j) / Ls[j * 65 + j]; if (tid == j) x0 = xj; }
-        else { xj = __shfl_sync(0xffffffffu, x1, j - 32) / Ls[j * 65 + j]; if (tid == j - 32) x1 = xj; }
-        if (tid > j) x0 -= Ls[tid * 65 + j] * xj;
-        if (tid + 32 > j) x1 -= Ls[(tid + 32) * 65 + j] * xj;
-      }
-      x[tid] = x0; x[tid + 32] = x1;
-    }
-    __syncthreads();
-    const double* P = Gc + (size_t)kb * CHOL_NB * np;
-    for (int i = (kb + 1) * CHOL_NB + tid; i < np; i += 256) {
-      double s = 0.0;
-#pragma unroll 8
-      for (int j = 0; j < CHOL_NB; ++j) s += P[(size_t)j * np + i] * x[j];
-      r[i] -= s;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < np; i += 256) rhs[(size_t)c * np + i] = r[i];
-}
+constexpr size_t TRSVB_SMEM = sizeof(double) * ((size_t)PB * PB_LD + 1024 + 2 * PB);
 
-__global__ void __launch_bounds__(256) k_trsv_bwd(const double* __restrict__ G, size_t chain_stride, int np,
-                                                  double* __restrict__ rhs) {
+__global__ void __launch_bounds__(256) k_trsv_bwd128(const double* __restrict__ G, size_t chain_stride, int np,
+                                                     double* __restrict__ rhs, const double* __restrict__ dinv_g) {
   extern __shared__ double sm[];
-  double* r = sm;
-  double* Ls = r + np;
+  double* Ls = sm;                     // [r][c] lower block
+  double* x = sm + PB * PB_LD;         // [np] solution so far (entries >= (J+1)*128 valid)
+  double* b = x + 1024;                // [128] current right-hand side
+  double* dinv = b + PB;               // [128]
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* Gc = G + (size_t)c * chain_stride;
-  for (int i = tid; i < np; i += 256) r[i] = rhs[(size_t)c * np + i];
-  const int T = np / CHOL_NB;
-  for (int kb = T - 1; kb >= 0; --kb) {
-    const double* D = Gc + (size_t)kb * CHOL_NB * np + (size_t)kb * CHOL_NB;
-    __syncthreads();
-    for (int id = tid; id < CHOL_NB * CHOL_NB; id += 256) {
-      const int rr = id & 63, cc = id >> 6;
-      Ls[rr * 65 + cc] = D[(size_t)cc * np + rr];
+  double* rc = rhs + (size_t)c * np;
+  const int T = np / PB;
+  for (int J = T - 1; J >= 0; --J) {
+    const int r0 = (J + 1) * PB, nrow = np - r0;
+    const double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
+    for (int id = tid; id < PB * PB; id += 256) {
+      const int r = id & (PB - 1), cc = id >> 7;
+      Ls[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
     }
-    __syncthreads();
-    double* x = r + kb * CHOL_NB;
-    if (tid < 32) {   // solve L11' x = b : x_j = (b_j - sum_{i>j} L[i][j] x_i) / L[j][j], j descending
-      double x0 = x[tid], x1 = x[tid + 32];
-      for (int j = CHOL_NB - 1; j >= 0; --j) {
-        double xj;
-        if (j < 32) { xj = __shfl_sync(0xffffffffu, x0, j) / Ls[j * 65 + j]; if (tid == j) x0 = xj; }
-        else { xj = __shfl_sync(0xffffffffu, x1, j - 32) / Ls[j * 65 + j]; if (tid == j - 32) x1 = xj; }
-        if (tid < j) x0 -= Ls[j * 65 + tid] * xj;
-        if (tid + 32 < j) x1 -= Ls[j * 65 + tid + 32] * xj;
-      }
-      x[tid] = x0; x[tid + 32] = x1;
-    }
-    __syncthreads();
-    // r[j] -= sum_{ii<64} L[kb*64+ii][j] x[ii] for every earlier column j: one warp per column, lanes over ii
-    const double xa = x[lane], xb = x[lane + 32];
-    for (int j = warp; j < kb * CHOL_NB; j += 8) {
-      const double* col = Gc + (size_t)j * np + (size_t)kb * CHOL_NB;
-      double s = col[lane] * xa + col[lane + 32] * xb;
+    if (tid < PB) dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
+    // b_j = w_j - sum_{i >= r0} L[i][J*128 + j] x_i : warp w owns columns 16w .. 16w+15, 8 at a time
+    for (int jj = warp * 16; jj < warp * 16 + 16; jj += 8) {
+      double acc[8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) r[j] -= s;
+      for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+      const double* col = Gc + (size_t)(J * PB + jj) * np + r0;
+      for (int i = lane; i < nrow; i += 32) {
+        const double xi = x[r0 + i];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += col[(size_t)u * np + i] * xi;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        double v = acc[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) b[jj + u] = rc[J * PB + jj + u] - v;
+      }
     }
+    __syncthreads();
+    // L_JJ' x_J = b : columns from the right; one warp, lane owns entries lane, lane+32, lane+64, lane+96
+    if (warp == 0) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = b[lane + 32 * u];
+#pragma unroll
+      for (int u = 3; u >= 0; --u) {
+        for (int src = 31; src >= 0; --src) {
+          const int j = 32 * u + src;
+          const double xj = __shfl_sync(0xffffffffu, v[u], src) * dinv[j];
+          const double* Lj = Ls + j * PB_LD;
+          if (lane == src) v[u] = xj;
+          else if (lane < src) v[u] -= Lj[lane + 32 * u] * xj;
+#pragma unroll
+          for (int uu = 0; uu < 4; ++uu)
+            if (uu < u) v[uu] -= Lj[lane + 32 * uu] * xj;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { x[J * PB + lane + 32 * u] = v[u]; rc[J * PB + lane + 32 * u] = v[u]; }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = tid; i < np; i += 256) rhs[(size_t)c * np + i] = r[i];
 }
 
 // symmetric copy of G (lower -> full) into the aux buffer, for the parity tests.  grid = (np, C)
@@ -406,46 +547,46 @@ void launch_x_times(const Engine& e, int trans, const double* in, double* out, d
 }
 
 void linalg_setup() {
-  cudaFuncSetAttribute(k_syrk<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
-  cudaFuncSetAttribute(k_syrk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
-  cudaFuncSetAttribute(k_trsv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  cudaFuncSetAttribute(k_trsv_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaFuncSetAttribute(k_gram_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  cudaFuncSetAttribute(k_potf2_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
+  cudaFuncSetAttribute(k_trsm_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+  cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSVB_SMEM);
 }
 
 void launch_syrk_G(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const int T = d.np / SY_BT;
   dim3 grid(T * (T + 1) / 2, d.C);
-  ++g_launches; k_syrk<0><<<grid, 256, SYRK_SMEM, s>>>(e.X, 0, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np,
-                                         d.qp / SY_BK, 0);
+  ++g_launches; k_gram_syrk<<<grid, 256, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np, d.qp / SY_BK);
   if (e.aux.G_copy) {
     dim3 g2(d.np, d.C);
     ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
   }
 }
 
+// factor every G_c in place AND forward-solve: rhs_c <- L_c^-1 rhs_c
 void launch_cholesky(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const size_t cs = (size_t)d.np * d.np;
-  const int T = d.np / CHOL_NB;
-  for (int kb = 0; kb < T; ++kb) {
-    ++g_launches; k_potf2<<<d.C, 256, 0, s>>>(e.G, cs, d.np, kb, e.status);
-    const int rows = d.np - (kb + 1) * CHOL_NB;
-    if (rows <= 0) break;
-    dim3 g1((rows + 127) / 128, d.C);
-    ++g_launches; k_trsm_panel<<<g1, 128, 0, s>>>(e.G, cs, d.np, kb);
-    const int Tt = (rows + SY_BT - 1) / SY_BT;
-    dim3 g2(Tt * (Tt + 1) / 2, d.C);
-    ++g_launches; k_syrk<1><<<g2, 256, SYRK_SMEM, s>>>(e.G + (size_t)kb * CHOL_NB * d.np, cs, d.np, nullptr, 0, e.G, cs, d.np,
-                                         CHOL_NB / SY_BK, (kb + 1) * CHOL_NB);
+  const int T = d.np / PB;
+  for (int J = 0; J < T; ++J) {
+    if (J > 0) {
+      dim3 g2(T - J, d.C);
+      ++g_launches; k_chol_update<<<g2, 256, SYRK_SMEM, s>>>(e.G, cs, d.np, e.G, d.np, J * PB / SY_BK, J);
+    }
+    ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, d.np, J, e.rhs, e.dinv, e.status);
+    if (J + 1 < T) {
+      dim3 g1(T - J - 1, d.C);
+      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, d.np, J, e.dinv);
+    }
   }
 }
 
+// rhs_c <- L_c^-T rhs_c  (the forward half already happened inside launch_cholesky)
 void launch_chol_solve(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
-  const size_t sm = sizeof(double) * ((size_t)d.np + CHOL_NB * 65);
-  ++g_launches; k_trsv_fwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
-  ++g_launches; k_trsv_bwd<<<d.C, 256, sm, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs);
+  ++g_launches; k_trsv_bwd128<<<d.C, 256, TRSVB_SMEM, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs, e.dinv);
 }
 
 }  // namespace bnr
