@@ -25,61 +25,285 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ------------------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA engine) helpers
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// contiguous global -> shared copy by the TMA engine, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // SYRK on FP64 tensor cores.
 //   MODE 0:  C_c[i][j] = sum_k A[i][k] s_c[k] A[j][k] + (i==j)      A = X (shared by all chains), K = qp
 //   MODE 1:  C_c[i][j] -= sum_{k < nk*16} L_c[i][k] L_c[j][k]        left-looking Cholesky update of block column J
 // The operand is "k-major": element (row, k) at A[row + ld*k] (rows contiguous) - exactly how X (column-major
-// n x q) and a column panel of the column-major G are stored, so tiles are staged with 16-byte cp.async and no
-// transposition.  CTA tile 128 x 128, k-step 16, 8 warps (2 along j x 4 along i), warp tile 64(j) x 32(i):
-// the MMA "M" dimension runs along j (columns of C) and "N" along i (rows of C), so every accumulator pair is two
-// consecutive rows of one column of the column-major C -> 16-byte stores.
-// grid = (lower-triangular tiles, C); dynamic smem = SYRK_SMEM.
+// n x q) and a column panel of the column-major G are stored, so a 128-row x 16-k tile is sixteen contiguous
+// 1 KB rows.  A dedicated producer warp streams them into a 4-stage shared-memory ring with TMA-engine bulk
+// copies (cp.async.bulk, completion on "full" mbarriers); the 8 consumer warps never execute a block-wide
+// barrier in the main loop - they wait on "full", issue DMMA m8n8k4, and release the stage on "empty".
+// CTA tile 128 x 128, k-step 16, consumer warps 2 (along j) x 4 (along i), warp tile 64(j) x 32(i): the MMA
+// "M" dimension runs along j (columns of C) and "N" along i (rows of C), so every accumulator pair is two
+// consecutive rows of one column of the column-major C -> 16-byte stores.  Shared rows are padded to 132
+// doubles (== 4 mod 16) which makes the (row, k) fragment loads bank-conflict free.
+// Work that cannot contribute is skipped: diagonal tiles compute only their lower triangle (balanced over the
+// warps, see syrk_diag_tile), and warp tiles that lie entirely in the zero padding beyond n are not issued.
+// grid = (C, tiles), block = 384 (2 consumer warpgroups + 1 producer warpgroup, registers re-balanced with
+// setmaxnreg: 232 per consumer thread, 40 per producer thread); dynamic smem = SYRK_SMEM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SY_BT = 128;        // tile edge
 constexpr int SY_BK = 16;         // k-step
 constexpr int SY_LDS = 132;       // smem row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
-constexpr int SY_STAGES = 3;
+constexpr int SY_STAGES = 4;
 constexpr int SY_STAGE_DBL = 2 * SY_BK * SY_LDS + SY_BK;   // two operand tiles + 16 scales
-constexpr size_t SYRK_SMEM = (size_t)SY_STAGES * SY_STAGE_DBL * sizeof(double);
+constexpr int SY_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgroup (one active lane)
+constexpr int SY_PRODUCER_REGS = 40, SY_CONSUMER_REGS = 232;   // 128*40 + 256*232 = 64512 = 384*168
+constexpr size_t SYRK_SMEM = (size_t)SY_STAGES * SY_STAGE_DBL * sizeof(double) + 2 * SY_STAGES * sizeof(unsigned long long);
+
+// fragments of one k4-step: 8 A fragments (rows of the j operand) and 4 scaled B fragments (rows of the i operand)
+template <int MODE>
+__device__ __forceinline__ void syrk_load_frags(const double* __restrict__ sj, const double* __restrict__ si,
+                                                const double* __restrict__ ss, int k4, int wj, int wi, int lk, int lr,
+                                                double (&af)[8], double (&bf)[4]) {
+  const int kr = k4 * 4 + lk;
+#ifdef SYRK_LAB_NOLDS
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf) af[mf] = 1.0 + mf + kr;
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) bf[nf] = 2.0 + nf + kr;
+#else
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf) af[mf] = sj[kr * SY_LDS + wj * 64 + mf * 8 + lr];
+#ifdef SYRK_LAB_NOSCALE
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) bf[nf] = si[kr * SY_LDS + wi * 32 + nf * 8 + lr];
+#else
+  const double sk = (MODE == 0) ? ss[kr] : 1.0;
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) bf[nf] = si[kr * SY_LDS + wi * 32 + nf * 8 + lr] * sk;
+#endif
+#endif
+}
+
+__device__ __forceinline__ void syrk_mma(double (&acc)[8][4][2], const double (&af)[8], const double (&bf)[4]) {
+#pragma unroll
+  for (int mf = 0; mf < 8; ++mf)
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+}
+
+// consumer main loop: fragments of k4-step t+1 are fetched from shared memory (and scaled) while the 32 DMMAs of
+// step t are in flight, across stage boundaries too, so no LDS / DMUL latency is exposed to the FP64 pipe.
+template <int MODE>
+__device__ __forceinline__ void syrk_mainloop(const double* __restrict__ smem, unsigned long long* full,
+                                              unsigned long long* empty, int nk, double (&acc)[8][4][2],
+                                              int wj, int wi, int lk, int lr, int lane) {
+  double af[2][8], bf[2][4];
+  auto stage_ptrs = [&](int kt, const double*& sj, const double*& si, const double*& ss) {
+    sj = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DBL;
+    si = sj + SY_BK * SY_LDS;
+    ss = sj + 2 * SY_BK * SY_LDS;
+  };
+  const double *sj, *si, *ss;
+  mbar_wait(&full[0], 0);
+  stage_ptrs(0, sj, si, ss);
+  syrk_load_frags<MODE>(sj, si, ss, 0, wj, wi, lk, lr, af[0], bf[0]);
+  for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (k4 + 1 < SY_BK / 4) {
+        syrk_load_frags<MODE>(sj, si, ss, k4 + 1, wj, wi, lk, lr, af[nxt], bf[nxt]);
+      } else if (kt + 1 < nk) {
+        const double *nj, *ni, *ns;
+        mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
+        stage_ptrs(kt + 1, nj, ni, ns);
+        syrk_load_frags<MODE>(nj, ni, ns, 0, wj, wi, lk, lr, af[nxt], bf[nxt]);
+      }
+      syrk_mma(acc, af[cur], bf[cur]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
+    stage_ptrs(kt + 1, sj, si, ss);
+  }
+}
+
+// Diagonal tiles: only the lower triangle of the 128 x 128 tile is needed.  Seen as 16 x 16 fragments of 8 x 8,
+// fragment column j holds 16 - j useful fragments; warp W takes columns W and 15 - W (17 fragments, the same for
+// every warp), so the symmetric half is skipped AND the four SM sub-partitions stay evenly loaded.  W is a template
+// parameter: every loop bound and register index is static, no predicated DMMA.
+// acc[t], t < 16-W : fragment (row-fragment W+t, column-fragment W);  t >= 16-W : (row-fragment t-1, column 15-W).
+template <int MODE, int W>
+__device__ __forceinline__ void syrk_diag_frags(const double* __restrict__ sj, const double* __restrict__ ss, int k4,
+                                                int lk, int lr, double (&a2)[2], double (&bfr)[16 - W]) {
+  const int kr = k4 * 4 + lk;
+  const double* row = sj + kr * SY_LDS + lr;
+  const double sk = (MODE == 0) ? ss[kr] : 1.0;
+  a2[0] = row[W * 8];
+  a2[1] = row[(15 - W) * 8];
+#pragma unroll
+  for (int i = 0; i < 16 - W; ++i) bfr[i] = row[(W + i) * 8] * sk;
+}
+
+template <int MODE, int W>
+__device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, unsigned long long* full,
+                                               unsigned long long* empty, int nk, int lk, int lr, int lane,
+                                               double* __restrict__ Cc, int np, int i0) {
+  constexpr int NA = 16 - W;        // fragments of column W
+  double acc[17][2];
+#pragma unroll
+  for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+  double a2[2][2], bfr[2][NA];
+  mbar_wait(&full[0], 0);
+  const double* sj = smem;
+  syrk_diag_frags<MODE, W>(sj, sj + 2 * SY_BK * SY_LDS, 0, lk, lr, a2[0], bfr[0]);
+  for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (k4 + 1 < SY_BK / 4) {
+        syrk_diag_frags<MODE, W>(sj, sj + 2 * SY_BK * SY_LDS, k4 + 1, lk, lr, a2[nxt], bfr[nxt]);
+      } else if (kt + 1 < nk) {
+        mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
+        const double* nj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
+        syrk_diag_frags<MODE, W>(nj, nj + 2 * SY_BK * SY_LDS, 0, lk, lr, a2[nxt], bfr[nxt]);
+      }
+#pragma unroll
+      for (int t = 0; t < NA; ++t) dmma884(acc[t][0], acc[t][1], a2[cur][0], bfr[cur][t]);
+#pragma unroll
+      for (int t = NA; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a2[cur][1], bfr[cur][t - 1 - W]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
+    sj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
+  }
+#pragma unroll
+  for (int t = 0; t < 17; ++t) {
+    const int jf = (t < NA) ? W : 15 - W;
+    const int ifr = (t < NA) ? W + t : t - 1;
+    const int j = i0 + jf * 8 + lr;                   // diagonal tile: j0 == i0
+    const int i = i0 + ifr * 8 + 2 * lk;
+    double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
+    double2 v;
+    if (MODE == 0) {
+      v.x = acc[t][0] + (i == j ? 1.0 : 0.0);
+      v.y = acc[t][1] + (i + 1 == j ? 1.0 : 0.0);
+    } else {
+      v = *p;
+      v.x -= acc[t][0];
+      v.y -= acc[t][1];
+    }
+    *p = v;
+  }
+}
 
 template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
-       size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nk, int origin) {
+          size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin) {
   extern __shared__ __align__(16) double smem[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
+  unsigned long long* empty = full + SY_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int c = blockIdx.y;
+  const int c = blockIdx.x;          // chains vary fastest: the 64 CTAs that share one X tile run back to back (L2 reuse)
   int ib, jb;
   if (MODE == 0) {
-    // lower-triangular tile enumeration: t -> (ib >= jb)
-    const int t = blockIdx.x;
-    ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
-    while (ib * (ib + 1) / 2 > t) --ib;
-    jb = t - ib * (ib + 1) / 2;
+    // blockIdx.y enumerates the lower-triangular tiles, the strictly-lower (full-cost) ones first and the
+    // diagonal (half-cost) ones last, so the tail of the grid is made of cheap CTAs
+    const int T = np / SY_BT, noff = T * (T - 1) / 2;
+#ifdef SYRK_LAB_ONLY_DIAG
+    const int t = blockIdx.y + noff;
+#else
+    const int t = blockIdx.y;
+#endif
+    if (t < noff) {
+      ib = (int)((1.0 + sqrt(1.0 + 8.0 * t)) * 0.5);
+      while (ib * (ib - 1) / 2 > t) --ib;
+      while ((ib + 1) * ib / 2 <= t) ++ib;
+      jb = t - ib * (ib - 1) / 2;
+    } else {
+      ib = jb = t - noff;
+    }
   } else {
-    // left-looking update of block column J = origin: tiles (J + blockIdx.x, J)
+    // left-looking update of block column J = origin: tiles (J+1 .. T-1, J) first, the diagonal tile (J, J) last
+    const int T = np / SY_BT, nt = T - origin;
     jb = origin;
-    ib = origin + blockIdx.x;
+    ib = (blockIdx.y == nt - 1) ? origin : origin + 1 + blockIdx.y;
   }
   const int i0 = ib * SY_BT, j0 = jb * SY_BT;
+  const bool diag = (ib == jb);
   const double* Ac = A + (size_t)c * a_chain_stride;
   const double* sc = (MODE == 0) ? scale + (size_t)c * scale_stride : nullptr;
 
-  auto load_stage = [&](int stage, int kt) {
-    double* sj = smem + (size_t)stage * SY_STAGE_DBL;
-    double* si = sj + SY_BK * SY_LDS;
-    const int kbase = kt * SY_BK;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int id = tid + 256 * r;
-      const int krow = id >> 6, c16 = id & 63;
-      const double* gsrc = Ac + (size_t)(kbase + krow) * ld;
-      cp_async16(sj + krow * SY_LDS + 2 * c16, gsrc + j0 + 2 * c16);
-      cp_async16(si + krow * SY_LDS + 2 * c16, gsrc + i0 + 2 * c16);
+  if (tid == 0) {
+    for (int s = 0; s < SY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= 8) {
+    // ---------------- producer warpgroup: hands its registers to the consumers, one lane drives the TMA engine ----
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SY_PRODUCER_REGS));
+    if (warp == 8 && lane == 0) {
+      const unsigned bytes = (diag ? 1u : 2u) * SY_BK * SY_BT * 8u + (MODE == 0 ? SY_BK * 8u : 0u);
+      for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt % SY_STAGES;
+        const unsigned ph = (kt / SY_STAGES) & 1;
+        mbar_wait(&empty[stage], ph ^ 1);
+        double* sj = smem + (size_t)stage * SY_STAGE_DBL;
+        double* si = sj + SY_BK * SY_LDS;
+        mbar_expect_tx(&full[stage], bytes);
+        const double* g = Ac + (size_t)kt * SY_BK * ld;
+#pragma unroll 4
+        for (int kr = 0; kr < SY_BK; ++kr) {
+          bulk_g2s(sj + kr * SY_LDS, g + (size_t)kr * ld + j0, SY_BT * 8, &full[stage]);
+          if (!diag) bulk_g2s(si + kr * SY_LDS, g + (size_t)kr * ld + i0, SY_BT * 8, &full[stage]);
+        }
+        if (MODE == 0) bulk_g2s(si + SY_BK * SY_LDS, sc + kt * SY_BK, SY_BK * 8, &full[stage]);
+      }
     }
-    if (MODE == 0 && tid < 8) cp_async16(si + SY_BK * SY_LDS + 2 * tid, sc + kbase + 2 * tid);
-  };
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(SY_CONSUMER_REGS));
+  const int lk = lane & 3, lr = lane >> 2;
+  double* Cc = Cm + (size_t)c * c_chain_stride;
+
+  if (diag) {
+    switch (warp) {
+      case 0: syrk_diag_tile<MODE, 0>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 1: syrk_diag_tile<MODE, 1>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 2: syrk_diag_tile<MODE, 2>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 3: syrk_diag_tile<MODE, 3>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 4: syrk_diag_tile<MODE, 4>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 5: syrk_diag_tile<MODE, 5>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 6: syrk_diag_tile<MODE, 6>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      default: syrk_diag_tile<MODE, 7>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+    }
+    return;
+  }
 
   double acc[8][4][2];
 #pragma unroll
@@ -88,73 +312,55 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   const int wj = warp >> 2, wi = warp & 3;
-  const int lk = lane & 3, lr = lane >> 2;
+  // fragments (8 rows) that hold at least one valid row; rows >= nvalid are zero padding
+  int mf_cnt = (nvalid - (j0 + wj * 64) + 7) / 8;
+  int nf_cnt = (nvalid - (i0 + wi * 32) + 7) / 8;
+  mf_cnt = mf_cnt < 0 ? 0 : (mf_cnt > 8 ? 8 : mf_cnt);
+  nf_cnt = nf_cnt < 0 ? 0 : (nf_cnt > 4 ? 4 : nf_cnt);
+  const bool all_pad = (mf_cnt == 0 || nf_cnt == 0);      // X rows there are zero: the product is exactly 0
 
-#pragma unroll
-  for (int s = 0; s < SY_STAGES - 1; ++s) {
-    if (s < nk) load_stage(s, s);
-    cp_async_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<SY_STAGES - 2>();
-    __syncthreads();
-    const int pre = kt + SY_STAGES - 1;
-    if (pre < nk) load_stage(pre % SY_STAGES, pre);
-    cp_async_commit();
-    const double* sj = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DBL;
-    const double* si = sj + SY_BK * SY_LDS;
-    const double* ss = si + SY_BK * SY_LDS;
-#pragma unroll
-    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
-      const int kr = k4 * 4 + lk;
-      double af[8], bf[4];
-#pragma unroll
-      for (int mf = 0; mf < 8; ++mf) af[mf] = sj[kr * SY_LDS + wj * 64 + mf * 8 + lr];
-      const double sk = (MODE == 0) ? ss[kr] : 1.0;
-#pragma unroll
-      for (int nf = 0; nf < 4; ++nf) bf[nf] = si[kr * SY_LDS + wi * 32 + nf * 8 + lr] * sk;
-#pragma unroll
-      for (int mf = 0; mf < 8; ++mf)
-#pragma unroll
-        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+  if (all_pad) {
+    // still take part in the stage hand-shake so the producer can recycle the ring
+    for (int kt = 0; kt < nk; ++kt) {
+      mbar_wait(&full[kt % SY_STAGES], (kt / SY_STAGES) & 1);
+      if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
     }
+  } else {
+    syrk_mainloop<MODE>(smem, full, empty, nk, acc, wj, wi, lk, lr, lane);
   }
-  cp_async_wait<0>();
+  if (all_pad && MODE == 1) return;        // nothing to subtract; MODE 0 still stores 0 (+ identity on a diagonal)
 
-  double* Cc = Cm + (size_t)c * c_chain_stride;
 #pragma unroll
   for (int mf = 0; mf < 8; ++mf) {
     const int j = j0 + wj * 64 + mf * 8 + lr;
 #pragma unroll
     for (int nf = 0; nf < 4; ++nf) {
       const int i = i0 + wi * 32 + nf * 8 + 2 * lk;
-      if (i < np && j < np) {
-        double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
-        double2 v;
-        if (MODE == 0) {
-          v.x = acc[mf][nf][0] + (i == j ? 1.0 : 0.0);
-          v.y = acc[mf][nf][1] + (i + 1 == j ? 1.0 : 0.0);
-        } else {
-          v = *p;
-          v.x -= acc[mf][nf][0];
-          v.y -= acc[mf][nf][1];
-        }
-        *p = v;
+      double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
+      double2 v;
+      if (MODE == 0) {
+        v.x = acc[mf][nf][0];
+        v.y = acc[mf][nf][1];
+      } else {
+        v = *p;
+        v.x -= acc[mf][nf][0];
+        v.y -= acc[mf][nf][1];
       }
+      *p = v;
     }
   }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(SY_THREADS, 1)
 k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ scale, size_t scale_stride,
-            double* __restrict__ G, size_t g_chain_stride, int np, int nk) {
-  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nk, 0);
+            double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk) {
+  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk, 0);
 }
 
-__global__ void __launch_bounds__(256, 1)
-k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nk,
-              int origin) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nk, origin);
+__global__ void __launch_bounds__(SY_THREADS, 1)
+k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
+              int nk, int origin) {
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -557,8 +763,15 @@ void linalg_setup() {
 void launch_syrk_G(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const int T = d.np / SY_BT;
-  dim3 grid(T * (T + 1) / 2, d.C);
-  ++g_launches; k_gram_syrk<<<grid, 256, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np, d.qp / SY_BK);
+#if defined(SYRK_LAB_ONLY_DIAG)
+  dim3 grid(d.C, T);
+#elif defined(SYRK_LAB_ONLY_OFFDIAG)
+  dim3 grid(d.C, T * (T - 1) / 2);
+#else
+  dim3 grid(d.C, T * (T + 1) / 2);
+#endif
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np, d.n,
+                                                            d.qp / SY_BK);
   if (e.aux.G_copy) {
     dim3 g2(d.np, d.C);
     ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
@@ -572,8 +785,8 @@ void launch_cholesky(const Engine& e, cudaStream_t s) {
   const int T = d.np / PB;
   for (int J = 0; J < T; ++J) {
     if (J > 0) {
-      dim3 g2(T - J, d.C);
-      ++g_launches; k_chol_update<<<g2, 256, SYRK_SMEM, s>>>(e.G, cs, d.np, e.G, d.np, J * PB / SY_BK, J);
+      dim3 g2(d.C, T - J);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, d.np, e.G, d.np, d.np, J * PB / SY_BK, J);
     }
     ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, d.np, J, e.rhs, e.dinv, e.status);
     if (J + 1 < T) {
