@@ -1,0 +1,158 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/bnr.h declares (no compute calls
+without a GPU), the ctypes prototypes cover the header, and the host-side Fit!/Summary logic (row bookkeeping of
+run!, purge_burn normalisation, Summary tables) behaves like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import bnr_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "bnr.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnr_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(bnr):
+    lib = ctypes.CDLL(os.path.join(ROOT, "bayesiannetworkregression.jl_b200", "libbnr.so"))
+    syms = _header_symbols()
+    assert len(syms) >= 30
+    for name in syms:
+        assert hasattr(lib, name), "libbnr.so does not export " + name
+    from bnr_b200 import capi
+    assert sorted(capi.PROTOTYPES) == syms, "ctypes prototypes and include/bnr.h disagree"
+    assert bnr.lib().bnr_version() == 100
+
+
+def test_params_struct_matches_header(bnr):
+    from bnr_b200 import capi
+    p = capi.Params()
+    bnr.lib().bnr_default_params(ctypes.byref(p))
+    assert (p.eta, p.zeta, p.iota, p.a_delta, p.b_delta, p.nu) == (1.01, 1.0, 1.0, 1.0, 1.0, 10.0)
+    assert p.num_chains == 2 and p.gig_inject_len == 64 and p.trace_full_chains == 1
+    assert ctypes.sizeof(capi.Params) == 8 * 4 + 8 + 8 + 6 * 8 + 8
+
+
+def test_no_gpu_is_a_loud_error(bnr):
+    """There is no CPU fallback: without a device bnr_create fails with BNR_ENODEV and a message."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    X = np.zeros((4, 10))
+    with pytest.raises(bnr.BnrError) as ei:
+        bnr.Engine(X, np.zeros(4), 3)
+    assert ei.value.code == -5 and "no CPU fallback" in str(ei.value)
+
+
+def test_bad_arguments_rejected_before_any_cuda_call(bnr):
+    from bnr_b200 import capi
+    L = bnr.lib()
+    assert L.bnr_create(None, None, None, None) == -1
+    assert b"null" in L.bnr_last_error()
+    with pytest.raises(ValueError):
+        bnr.Engine(np.zeros((4, 11)), np.zeros(4), 3)        # 11 is not V(V+1)/2
+    with pytest.raises(ValueError):
+        bnr.Fit(np.zeros((4, 10)), np.zeros(4), 12, ν=10, x_transform=False, filename=None)   # nu < R
+
+
+class FakeEngine:
+    """Records what the host logic asks of the engine (rows written, copies)."""
+
+    def __init__(self, rows):
+        self.table = [None] * rows
+        self.trace_row = 0
+        self.sweep = 0
+        self.table[0] = 0
+
+    def run(self, n):
+        for _ in range(n):
+            self.sweep += 1
+            if self.trace_row < len(self.table):
+                self.table[self.trace_row] = self.sweep
+            self.trace_row += 1
+
+    def copy_trace_rows(self, dst, src, count=1):
+        self.table[dst:dst + count] = self.table[src:src + count]
+
+
+def _reference_run(table, first_index, nburn, total, purge_burn, sweep):
+    """Literal run! (src/gibbs.jl:849-864), 1-based."""
+    j = first_index
+    for i in range(first_index, total + 1):
+        sweep += 1
+        table[j - 1] = sweep
+        if purge_burn is not None and i < nburn and j == purge_burn + 1:
+            table[0] = table[j - 1]
+            j = 1
+        j += 1
+    return sweep
+
+
+@pytest.mark.parametrize("nburn,nsamp,purge", [(40, 30, None), (40, 30, 10), (40, 30, 7), (100, 20, 25), (12, 50, 5)])
+def test_run_rows_matches_reference_loop(bnr, nburn, nsamp, purge):
+    from bnr_b200 import fit
+    pb = fit._normalise_purge(purge, nburn)
+    total = nburn + nsamp
+    rows = total if pb is None else nsamp + pb
+    eng = FakeEngine(rows)
+    eng.trace_row = 1
+    fit._run_rows(eng, 2, nburn, total, pb)
+    want = [None] * rows
+    want[0] = 0
+    _reference_run(want, 2, nburn, total, pb, 0)
+    assert eng.table == want
+    assert eng.sweep == total - 1
+    # the retained rows are the last nsamp sweeps
+    nb = pb if pb is not None else nburn
+    assert eng.table[nb:nb + nsamp] == list(range(total - nsamp, total))
+
+
+def test_purge_normalisation(bnr):
+    from bnr_b200 import fit
+    assert fit._normalise_purge(None, 100) is None
+    assert fit._normalise_purge(0, 100) is None
+    assert fit._normalise_purge(100, 100) is None          # not < nburn
+    assert fit._normalise_purge(10, 100) == 10
+    assert fit._normalise_purge(30, 100) == 30 - 100 % 30  # src/gibbs.jl:931-933
+
+
+def test_summary_matches_goldens(bnr, golden):
+    """Host-side Summary == the reference's stored `out2` table when fed the reference's stored traces."""
+    st = bnr.Table(gamma=golden["res2.gamma"], xi=golden["res2.xi"])
+    res = bnr.Results(st, golden["res2.rhat_xi"], golden["res2.rhat_gamma"], 200, 200)
+    out = bnr.Summary(res)
+    for k in ("node1", "node2", "estimate", "lower_bound", "upper_bound"):
+        np.testing.assert_array_equal(out.edge_coef[k], golden["out2." + k], err_msg=k)
+    np.testing.assert_array_equal(out.prob_nodes["probability"], golden["out2.probability"])
+    assert "Edge Coefficient Estimates (95% credible intervals)" in repr(out)
+    out90 = bnr.Summary(res, interval=90, digits=2)
+    want = O.summary(golden["res2.gamma"][200:400, :, 0], golden["res2.xi"][200:400, :, 0], interval=90, digits=2)
+    np.testing.assert_array_equal(out90.edge_coef["lower_bound"], want["lower_bound"])
+
+
+def test_setup_X_and_index_maps(bnr):
+    rng = np.random.default_rng(0)
+    mats = []
+    for _ in range(5):
+        A = rng.random((6, 6))
+        mats.append(A + A.T)
+    Xn = bnr.setup_X(mats)
+    assert Xn.shape == (5, 21)
+    np.testing.assert_array_equal(Xn, O.setup_X(mats))
+    np.testing.assert_array_equal(bnr.create_lower_tri(Xn[0], 6), np.tril(mats[0]))
+    np.testing.assert_array_equal(bnr.lower_triangle(mats[1]), O.lower_triangle(mats[1]))
+    with pytest.raises(ValueError):
+        bnr.lower_triangle(np.zeros((2, 3)))
+
+
+def test_table_aliases(bnr):
+    t = bnr.Table(gamma=np.zeros((3, 2, 1)), xi=np.ones((3, 4, 1)), tau2=np.zeros((3, 1, 1)), pi=np.zeros((3, 2, 3)))
+    assert t["γ"] is t["gamma"] is t.gamma is t.γ
+    assert t["ξ"] is t.xi and t["τ²"] is t.tau2 and t["πᵥ"] is t.pi
+    assert len(t) == 3
