@@ -367,25 +367,25 @@ k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double*
 // Blocked left-looking Cholesky, block size 128, with the forward solve L w = rhs folded in.
 //   for J = 0 .. np/128-1:
 //     k_chol_update   (DMMA, above):  G[J.., J] -= L[J.., 0:J] L[J, 0:J]'
-//     k_potf2_128     one CTA per chain: rhs_J -= L[J, 0:J] w[0:J]; factor the 128 x 128 diagonal block in shared
+//     k_potf2_128     one CTA per chain: factor the 128 x 128 diagonal block in shared
 //                     memory (4 sub-blocks of 32: a warp factors 32 x 32 in registers with shuffles, threads eliminate
 //                     the rows below, everybody updates the trailing part in 2 x 2 register tiles); rhs_J rides along as
 //                     row 128, so w_J = L_JJ^-1 rhs_J comes out of the same elimination.  1/L_jj goes to `dinv`.
 //     k_trsm_128      rows below the diagonal block: L[i, J] = G[i, J] L_JJ^-T, one thread per row, two 64-column
-//                     halves, right-looking inside the thread (independent FMAs, no divisions).
+//                     halves, right-looking inside the thread (independent FMAs, no divisions); the same thread then
+//                     subtracts its row's share of the forward solve: rhs[i] -= L[i, J] w_J.
 // All inner loops are arranged so that consecutive FP64 FMAs are independent: these kernels are latency-bound.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;            // panel / diagonal block size
 constexpr int PB_LD = PB + 1;      // shared-memory row stride of the (PB+1) x PB working block
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)(PB + 1) * PB_LD + 1024 + 32);
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)(PB + 1) * PB_LD + 32);
 
 __global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_t chain_stride, int np, int J,
                                                    double* __restrict__ rhs, double* __restrict__ dinv_out,
                                                    int* status) {
   extern __shared__ double sm[];
   double* A = sm;                          // A[r][c] at A[r * PB_LD + c], rows 0..128 (row 128 = rhs), cols 0..127
-  double* wprev = sm + (PB + 1) * PB_LD;   // [<= 1024] previously solved w (J*128 entries used)
-  double* dinv = wprev + 1024;             // [32] reciprocal diagonal of the current 32-block
+  double* dinv = sm + (PB + 1) * PB_LD;    // [32] reciprocal diagonal of the current 32-block
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Gc = G + (size_t)c * chain_stride;
   double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
@@ -395,26 +395,9 @@ __global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_
     const int r = id & (PB - 1), cc = id >> 7;
     A[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
   }
-  for (int k = tid; k < kprev; k += 256) wprev[k] = rc[k];
-  __syncthreads();
-  // rhs_J -= L[J-block rows, 0:kprev] w[0:kprev]  (thread (jj, half) walks half of the columns; coalesced in jj)
-  {
-    const int jj = tid & (PB - 1), half = tid >> 7;
-    const double* Lrow = Gc + (size_t)J * PB + jj;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const int k0 = half * (kprev / 2), k1 = half ? kprev : kprev / 2;
-    for (int k = k0; k < k1; k += 4) {      // kprev is a multiple of 128
-      a0 += Lrow[(size_t)k * np] * wprev[k];
-      a1 += Lrow[(size_t)(k + 1) * np] * wprev[k + 1];
-      a2 += Lrow[(size_t)(k + 2) * np] * wprev[k + 2];
-      a3 += Lrow[(size_t)(k + 3) * np] * wprev[k + 3];
-    }
-    const double acc = (a0 + a1) + (a2 + a3);
-    double* part = A + PB * PB_LD;          // row 128 of the working block
-    if (half == 0) part[jj] = rc[kprev + jj] - acc;
-    __syncthreads();
-    if (half == 1) part[jj] -= acc;
-  }
+  // rhs rides along as row 128 of the working block; contributions of earlier panels were already subtracted
+  // by k_trsm_128 (right-looking forward solve), so w_J = L_JJ^-1 rhs_J falls out of the elimination below
+  if (tid < PB) A[PB * PB_LD + tid] = rc[kprev + tid];
   __syncthreads();
   bool bad = false;
   for (int s = 0; s < PB / 32; ++s) {
@@ -499,16 +482,42 @@ __global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_
 }
 
 // rows below the diagonal block.  grid = (rows_below / 128, C), block = 128.
-// shared: Lt11, Lt21, Lt22 as [p][j] (column p of the 64 x 64 sub-block contiguous in j) + 128 reciprocal diagonals
-constexpr size_t TRSM_SMEM = sizeof(double) * (3 * 64 * 64 + 128);
+// shared: Lt11, Lt21, Lt22 as [p][j] (column p of the 64 x 64 sub-block contiguous in j, read as 16-byte broadcasts),
+// 128 reciprocal diagonals and w_J.
+constexpr size_t TRSM_SMEM = sizeof(double) * (3 * 64 * 64 + 256);
+
+// x[k] -= xj * l[k] for k = K0 .. 63 with 16-byte shared loads (K0 is a compile-time constant)
+template <int K0>
+__device__ __forceinline__ void axpy_tail(double (&x)[64], double xj, const double* __restrict__ l) {
+  constexpr int KE = (K0 + 1) & ~1;                    // first even index >= K0
+  if (K0 & 1) x[K0] -= xj * l[K0];
+  const double2* lv = reinterpret_cast<const double2*>(l);
+#pragma unroll
+  for (int k2 = KE / 2; k2 < 32; ++k2) {
+    const double2 v = lv[k2];
+    x[2 * k2] -= xj * v.x;
+    x[2 * k2 + 1] -= xj * v.y;
+  }
+}
+
+template <int J0>
+__device__ __forceinline__ void trsm_solve64(double (&x)[64], const double* __restrict__ Lt, const double* __restrict__ dinv) {
+  if constexpr (J0 < 64) {
+    const double xj = x[J0] * dinv[J0];
+    x[J0] = xj;
+    if constexpr (J0 + 1 < 64) axpy_tail<J0 + 1>(x, xj, Lt + J0 * 64);
+    trsm_solve64<J0 + 1>(x, Lt, dinv);
+  }
+}
 
 __global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t chain_stride, int np, int J,
-                                                  const double* __restrict__ dinv_g) {
-  extern __shared__ double sm[];
+                                                  const double* __restrict__ dinv_g, double* __restrict__ rhs) {
+  extern __shared__ __align__(16) double sm[];
   double* L11 = sm;                 // [p][j] = L11[j][p]
   double* L21 = sm + 64 * 64;       // [p][j] = L21[j][p]   (j: second-half column, p: first-half column)
   double* L22 = sm + 2 * 64 * 64;
-  double* dinv = sm + 3 * 64 * 64;
+  double* dinv = sm + 3 * 64 * 64;  // [128]
+  double* wJ = dinv + 128;          // [128]
   const int c = blockIdx.y, tid = threadIdx.x;
   double* Gc = G + (size_t)c * chain_stride;
   const double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
@@ -519,6 +528,7 @@ __global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t
     L22[cc * 64 + r] = D[(size_t)(64 + cc) * np + 64 + r];
   }
   dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
+  wJ[tid] = rhs[(size_t)c * np + J * PB + tid];
   __syncthreads();
   const int row = (J + 1) * PB + blockIdx.x * 128 + tid;
   if (row >= np) return;
@@ -527,17 +537,10 @@ __global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t
   double x[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) x[j] = prow[(size_t)j * np];
-  // first half: x_j = a_j / L11[j][j]; a_k -= x_j L11[k][j] (k > j)
+  trsm_solve64<0>(x, L11, dinv);            // first half: x_j = a_j / L11[j][j]; a_k -= x_j L11[k][j] (k > j)
+  double racc = 0.0;
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const double xj = x[j] * dinv[j];
-    x[j] = xj;
-    const double* l1 = L11 + j * 64;
-#pragma unroll
-    for (int k = j + 1; k < 64; ++k) x[k] -= xj * l1[k];
-  }
-#pragma unroll
-  for (int j = 0; j < 64; ++j) prow[(size_t)j * np] = x[j];
+  for (int j = 0; j < 64; ++j) { prow[(size_t)j * np] = x[j]; racc += x[j] * wJ[j]; }
   // second half, 16 columns at a time: y_k = A[row][64 + k] - sum_p x_p L21[k][p]
 #pragma unroll 1
   for (int k0 = 0; k0 < 64; k0 += 16) {
@@ -546,25 +549,24 @@ __global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t
     for (int k = 0; k < 16; ++k) y[k] = prow2[(size_t)(k0 + k) * np];
 #pragma unroll
     for (int p = 0; p < 64; ++p) {
-      const double* l2 = L21 + p * 64 + k0;
+      const double2* l2 = reinterpret_cast<const double2*>(L21 + p * 64 + k0);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) y[k] -= x[p] * l2[k];
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const double2 v = l2[k2];
+        y[2 * k2] -= x[p] * v.x;
+        y[2 * k2 + 1] -= x[p] * v.y;
+      }
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) prow2[(size_t)(k0 + k) * np] = y[k];
   }
 #pragma unroll
   for (int j = 0; j < 64; ++j) x[j] = prow2[(size_t)j * np];
+  trsm_solve64<0>(x, L22, dinv + 64);
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const double yj = x[j] * dinv[64 + j];
-    x[j] = yj;
-    const double* l2 = L22 + j * 64;
-#pragma unroll
-    for (int k = j + 1; k < 64; ++k) x[k] -= yj * l2[k];
-  }
-#pragma unroll
-  for (int j = 0; j < 64; ++j) prow2[(size_t)j * np] = x[j];
+  for (int j = 0; j < 64; ++j) { prow2[(size_t)j * np] = x[j]; racc += x[j] * wJ[64 + j]; }
+  // right-looking forward solve: this row's right-hand side loses the contribution of panel J
+  rhs[(size_t)c * np + row] -= racc;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -593,19 +595,20 @@ __global__ void __launch_bounds__(256) k_trsv_bwd128(const double* __restrict__ 
       Ls[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
     }
     if (tid < PB) dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
-    // b_j = w_j - sum_{i >= r0} L[i][J*128 + j] x_i : warp w owns columns 16w .. 16w+15, 8 at a time
-    for (int jj = warp * 16; jj < warp * 16 + 16; jj += 8) {
-      double acc[8];
+    // b_j = w_j - sum_{i >= r0} L[i][J*128 + j] x_i : warp w owns columns 16w .. 16w+15, all 16 in flight
+    {
+      const int jj = warp * 16;
+      double acc[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+      for (int u = 0; u < 16; ++u) acc[u] = 0.0;
       const double* col = Gc + (size_t)(J * PB + jj) * np + r0;
       for (int i = lane; i < nrow; i += 32) {
         const double xi = x[r0 + i];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] += col[(size_t)u * np + i] * xi;
+        for (int u = 0; u < 16; ++u) acc[u] += col[(size_t)u * np + i] * xi;
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 16; ++u) {
         double v = acc[u];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -791,7 +794,7 @@ void launch_cholesky(const Engine& e, cudaStream_t s) {
     ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, d.np, J, e.rhs, e.dinv, e.status);
     if (J + 1 < T) {
       dim3 g1(T - J - 1, d.C);
-      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, d.np, J, e.dinv);
+      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, d.np, J, e.dinv, e.rhs);
     }
   }
 }
