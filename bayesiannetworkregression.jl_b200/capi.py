@@ -19,7 +19,7 @@ class Params(C.Structure):
                 ("trace_gamma_xi_all", C.c_int32), ("trace_rows", C.c_int64), ("seed", C.c_uint64),
                 ("eta", C.c_double), ("zeta", C.c_double), ("iota", C.c_double), ("a_delta", C.c_double),
                 ("b_delta", C.c_double), ("nu", C.c_double), ("gig_inject_len", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("gamma_mode", C.c_int32)]
 
 
 VAR = dict(tau2=0, u=1, xi=2, gamma=3, S=4, theta=5, Delta=6, M=7, mu=8, lam=9, pi=10)
@@ -27,6 +27,7 @@ COND = dict(tau2=0, u_xi=1, gamma=2, D=3, theta=4, Delta=5, M=6, mu=7, lam=8, pi
 AUX = dict(tau2_params=0, sigma_inv=1, sigma_chol=2, mu_t=3, log_odds=4, W=5, G=6, G_chol=7, rhs=8, a4=9, chi=10,
            theta_params=11, delta_params=12, m_params=13, mu_params=14, lambda_logw=15, lambda_weights=16,
            pi_alpha=17, gig_used=18)
+GAMMA_MODE = dict(auto=0, nform=1, qform=2)
 STATUS_BITS = dict(jitter=1, sigma_notpd=2, g_notpd=4, gig_cap=8, inj_exhausted=16, nan=32, psi_notpd=64)
 
 _H = C.c_void_p
@@ -60,6 +61,7 @@ PROTOTYPES = {
     "bnr_get_trace": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _DP]),
     "bnr_status": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_export_moments": (C.c_int, [_H, C.c_void_p]),
+    "bnr_gamma_mode": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_launch_count": (C.c_int, [_H, _I64P]),
     "bnr_profile_sweep": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "bnr_set_injection": (C.c_int, [_H, _DP, C.c_int64]),

@@ -123,6 +123,19 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   d.q = p->V * (p->V + 1) / 2;
   d.np = (p->n + TILE_N - 1) / TILE_N * TILE_N;
   d.qp = (d.q + TILE_K - 1) / TILE_K * TILE_K;
+  // gamma draw formulation (SURVEY 8d cost model): the q x q precision form costs q^3/3 + 4q^2 flops per
+  // chain-iteration, the n x n Bhattacharya form (what the reference runs, src/gibbs.jl:429-436) n^2 q + n^3/3.
+  {
+    const double qd = d.q, nd = d.n;
+    const double cost_q = qd * qd * qd / 3.0 + 4.0 * qd * qd, cost_n = nd * nd * qd + nd * nd * nd / 3.0;
+    const int qp128 = (d.q + TILE_N - 1) / TILE_N * TILE_N;
+    int mode = p->gamma_mode;
+    if (mode != BNR_GAMMA_NFORM && mode != BNR_GAMMA_QFORM)
+      mode = (cost_q < cost_n && qp128 <= chol_max_dim()) ? BNR_GAMMA_QFORM : BNR_GAMMA_NFORM;
+    d.gmode = mode;
+    if (mode == BNR_GAMMA_QFORM) d.qp = qp128;       // q-padded vectors double as right-hand sides of the q x q solve
+    d.gdim = mode == BNR_GAMMA_QFORM ? d.qp : d.np;
+  }
   d.nparts = (d.q + PART_BLOCK - 1) / PART_BLOCK;
   d.chain_offset = p->chain_offset;
   d.gigK = h->p.gig_inject_len;
@@ -130,9 +143,9 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   d.eta = p->eta; d.zeta = p->zeta; d.iota = p->iota; d.a_delta = p->a_delta; d.b_delta = p->b_delta; d.nu = p->nu;
   // dynamic shared memory of the per-chain kernels grows with V*R
   const size_t need = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + 4 * (2 * d.V + 2 * d.R * d.R + 3 * d.R));
-  if (need > 200 * 1024 || d.np > 1024) {
+  if (need > 200 * 1024 || d.gdim > chol_max_dim()) {
     delete h;
-    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R, or n > 1024)");
+    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R, or factored dimension > 4096)");
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -166,8 +179,26 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   DA(e.mu, C); DA(e.lambda, C * d.R); DA(e.pi, C * 3 * d.R);
   DA(e.W, C * d.qp); DA(e.v, C * d.qp); DA(e.t, C * d.qp);
   DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
-  DA(e.G, C * d.np * d.np + 2048);
-  DA(e.dinv, C * d.np);
+  DA(e.G, C * d.gdim * d.gdim + 2048);
+  DA(e.dinv, C * d.gdim);
+  e.XtX = nullptr;
+  if (d.gmode == BNR_GAMMA_QFORM) {
+    // X'X once: row-major copy of X as the SYRK operand (k-major over the n samples), unit scales, no identity
+    std::vector<double> xt((size_t)d.np * d.qp, 0.0), ones((size_t)d.np, 1.0);
+    for (int j = 0; j < d.q; ++j)
+      for (int i = 0; i < d.n; ++i) xt[(size_t)i * d.qp + j] = X[(size_t)i + (size_t)d.n * j];
+    double *dXT = nullptr, *dOnes = nullptr, *dXtX = nullptr;
+    CK(cudaMalloc((void**)&dXT, xt.size() * sizeof(double)));
+    CK(cudaMalloc((void**)&dOnes, ones.size() * sizeof(double)));
+    DA(dXtX, (size_t)d.qp * d.qp);
+    CK(cudaMemcpyAsync(dXT, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dOnes, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    launch_xtx(d, dXT, dOnes, dXtX, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(dXT));
+    CK(cudaFree(dOnes));
+    e.XtX = dXtX;
+  }
   DA(e.partials, C * d.nparts * (2 * MAX_R + 1));
   DA(e.status, C);
   DA(e.iter, 1); DA(e.trace_row, 1);
@@ -227,12 +258,24 @@ static void refresh_xg(bnr_handle* h) {
 static void run_gamma(bnr_handle* h, int gig_flags) {
   Engine& e = h->e;
   cudaStream_t s = h->stream;
+  if (e.d.gmode == BNR_GAMMA_QFORM) {
+    // P = (X'X + D^-1)/tau2 = L L';  L w = X'(y - mu - X W)/tau2;  L' beta = w + z;  gamma = W + beta
+    launch_edge_prep(e, 2, s);                        // W, v = z
+    launch_x_times(e, 0, e.W, e.xv, h->ws, s);        // X W
+    launch_rhs(e, s);                                 // (y - mu - X W)/tau2
+    launch_x_times(e, 1, e.rhs, e.t, h->ws, s);       // t = X' rhs
+    launch_build_P(e, s);
+    launch_cholesky(e, e.t, s);
+    launch_chol_solve(e, e.t, e.v, s);
+    launch_gamma_gig(e, (gig_flags & ~1) | ((gig_flags & 1) ? 4 : 0), s);
+    return;
+  }
   launch_edge_prep(e, 1, s);
   launch_x_times(e, 0, e.v, e.xv, h->ws, s);
   launch_rhs(e, s);
   launch_syrk_G(e, s);
-  launch_cholesky(e, s);
-  launch_chol_solve(e, s);
+  launch_cholesky(e, e.rhs, s);
+  launch_chol_solve(e, e.rhs, nullptr, s);
   launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
   launch_gamma_gig(e, gig_flags, s);
 }
@@ -627,7 +670,7 @@ extern "C" int bnr_enable_aux(bnr_handle* h, int32_t on) {
     DA(e.aux.mu_t, C * d.V * d.R); DA(e.aux.log_odds, C * d.V); DA(e.aux.chi, C * d.qp);
     DA(e.aux.theta_params, C * 2); DA(e.aux.delta_params, C * 2); DA(e.aux.m_params, C * (1 + 2 * d.R * d.R));
     DA(e.aux.mu_params, C * 2); DA(e.aux.lambda_logw, C * 3 * d.R); DA(e.aux.lambda_w, C * 3 * d.R);
-    DA(e.aux.pi_alpha, C * 3 * d.R); DA(e.aux.gig_used, C * d.qp); DA(e.aux.G_copy, C * d.np * d.np);
+    DA(e.aux.pi_alpha, C * 3 * d.R); DA(e.aux.gig_used, C * d.qp); DA(e.aux.G_copy, C * d.gdim * d.gdim);
     CK(cudaStreamSynchronize(h->stream));
   }
   h->aux_on = true;
@@ -650,7 +693,10 @@ extern "C" int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double*
     case BNR_AUX_MU_T: src = e.aux.mu_t + (size_t)chain * V * R; n = (size_t)V * R; break;
     case BNR_AUX_LOG_ODDS: src = e.aux.log_odds + (size_t)chain * V; n = V; break;
     case BNR_AUX_W: src = e.W + (size_t)chain * d.qp; n = d.q; break;
-    case BNR_AUX_RHS: case BNR_AUX_A4: src = e.rhs + (size_t)chain * d.np; n = d.n; break;
+    case BNR_AUX_RHS: case BNR_AUX_A4:
+      if (d.gmode == BNR_GAMMA_QFORM) { src = e.t + (size_t)chain * d.qp; n = d.q; }   // beta = gamma - W
+      else { src = e.rhs + (size_t)chain * d.np; n = d.n; }
+      break;
     case BNR_AUX_CHI: src = e.aux.chi + (size_t)chain * d.qp; n = d.q; break;
     case BNR_AUX_THETA_PARAMS: src = e.aux.theta_params + 2 * chain; n = 2; break;
     case BNR_AUX_DELTA_PARAMS: src = e.aux.delta_params + 2 * chain; n = 2; break;
@@ -661,17 +707,18 @@ extern "C" int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double*
     case BNR_AUX_PI_ALPHA: src = e.aux.pi_alpha + (size_t)chain * 3 * R; n = 3 * R; break;
     case BNR_AUX_GIG_USED: src = e.aux.gig_used + (size_t)chain * d.qp; n = d.q; break;
     case BNR_AUX_G: case BNR_AUX_G_CHOL: {
-      // n x n sub-block of the padded np x np matrix
-      const double* base = (aux_id == BNR_AUX_G ? e.aux.G_copy : e.G) + (size_t)chain * d.np * d.np;
-      if (capacity < (int64_t)d.n * d.n) return fail(BNR_EINVAL, "capacity too small");
-      tmp.resize((size_t)d.np * d.np);
+      // m x m sub-block of the padded gdim x gdim matrix (m = n in the n-form, q in the q-form)
+      const int m = d.gmode == BNR_GAMMA_QFORM ? d.q : d.n, N = d.gdim;
+      const double* base = (aux_id == BNR_AUX_G ? e.aux.G_copy : e.G) + (size_t)chain * N * N;
+      if (capacity < (int64_t)m * m) return fail(BNR_EINVAL, "capacity too small");
+      tmp.resize((size_t)N * N);
       CK(cudaMemcpyAsync(tmp.data(), base, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
-      for (int j = 0; j < d.n; ++j)
-        for (int i = 0; i < d.n; ++i) {
-          double v = tmp[(size_t)j * d.np + i];
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+          double v = tmp[(size_t)j * N + i];
           if (aux_id == BNR_AUX_G_CHOL && i < j) v = 0.0;
-          out[(size_t)j * d.n + i] = v;
+          out[(size_t)j * m + i] = v;
         }
       return BNR_OK;
     }
@@ -757,6 +804,12 @@ extern "C" int bnr_rng_gamma(bnr_handle* h, int32_t chain, int64_t iteration, in
   return rng_dump(h, chain, iteration, site, element, 2, shape, count, out);
 }
 
+extern "C" int bnr_gamma_mode(bnr_handle* h, int32_t* mode) {
+  if (!h || !mode) return fail(BNR_EINVAL, "null argument");
+  *mode = h->e.d.gmode;
+  return BNR_OK;
+}
+
 extern "C" int bnr_launch_count(bnr_handle* h, int64_t* kernels) {
   if (!h || !kernels) return fail(BNR_EINVAL, "null argument");
   *kernels = h->launches;
@@ -789,18 +842,33 @@ extern "C" int bnr_profile_sweep(bnr_handle* h, float* ms) {
   launch_uxi(e, s);
   std::swap(e.u, e.u_alt);
   CK(cudaEventRecord(ev[2], s));
-  launch_edge_prep(e, 1, s);
-  launch_x_times(e, 0, e.v, e.xv, h->ws, s);
-  launch_rhs(e, s);
-  CK(cudaEventRecord(ev[3], s));
-  launch_syrk_G(e, s);
-  CK(cudaEventRecord(ev[4], s));
-  launch_cholesky(e, s);
-  CK(cudaEventRecord(ev[5], s));
-  launch_chol_solve(e, s);
-  CK(cudaEventRecord(ev[6], s));
-  launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
-  launch_gamma_gig(e, 3, s);
+  if (e.d.gmode == BNR_GAMMA_QFORM) {
+    launch_edge_prep(e, 2, s);
+    launch_x_times(e, 0, e.W, e.xv, h->ws, s);
+    launch_rhs(e, s);
+    launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
+    CK(cudaEventRecord(ev[3], s));
+    launch_build_P(e, s);
+    CK(cudaEventRecord(ev[4], s));
+    launch_cholesky(e, e.t, s);
+    CK(cudaEventRecord(ev[5], s));
+    launch_chol_solve(e, e.t, e.v, s);
+    CK(cudaEventRecord(ev[6], s));
+    launch_gamma_gig(e, 6, s);
+  } else {
+    launch_edge_prep(e, 1, s);
+    launch_x_times(e, 0, e.v, e.xv, h->ws, s);
+    launch_rhs(e, s);
+    CK(cudaEventRecord(ev[3], s));
+    launch_syrk_G(e, s);
+    CK(cudaEventRecord(ev[4], s));
+    launch_cholesky(e, e.rhs, s);
+    CK(cudaEventRecord(ev[5], s));
+    launch_chol_solve(e, e.rhs, nullptr, s);
+    CK(cudaEventRecord(ev[6], s));
+    launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
+    launch_gamma_gig(e, 3, s);
+  }
   CK(cudaEventRecord(ev[7], s));
   launch_x_times(e, 0, e.gamma, e.xg, h->ws, s);
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |

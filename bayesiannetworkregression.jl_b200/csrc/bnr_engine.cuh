@@ -14,7 +14,9 @@ constexpr int PART_BLOCK = 256;  // threads per block of the edge kernels (parti
 
 struct Dims {
   int n, V, R, q, C;
-  int np, qp;         // padded n (multiple of TILE_N) and q (multiple of TILE_K)
+  int np, qp;         // padded n (multiple of TILE_N) and q (multiple of TILE_K; of TILE_N in the q-form)
+  int gmode;          // gamma draw: 1 = n x n Bhattacharya form (G = X D X' + I), 2 = q x q precision form
+  int gdim;           // dimension of the matrix that is factored every sweep: np (n-form) or qp (q-form)
   int nparts;         // edge-kernel blocks per chain = ceil(q / PART_BLOCK)
   int chain_offset;
   int gigK;           // injected uniforms per edge
@@ -79,7 +81,7 @@ struct Aux {           // optional intermediate outputs for parity tests (nullpt
   double* lambda_w;      // [C][R*3]
   double* pi_alpha;      // [C][R*3]
   double* gig_used;      // [C][qp]
-  double* G_copy;        // [C][np*np]  X D X' + I before factorisation
+  double* G_copy;        // [C][gdim*gdim]  X D X' + I (n-form) or P (q-form) before factorisation
 };
 
 struct Engine {
@@ -88,6 +90,7 @@ struct Engine {
   const double* X;        // [qp][np] : column j of X padded to np rows (zeros beyond n and beyond q)
   const double* y;        // [np]
   const int2* edge_lk;    // [q] (l, k) of edge j, l >= k
+  const double* XtX;      // [qp][qp] X'X, lower triangle, column-major (q-form only, computed once)
   // state, [C][...]
   double* tau2; double* u; double* u_alt; double* xi; double* gamma; double* S; double* theta;
   double* Delta; double* M; double* mu; double* lambda; double* pi;
@@ -97,9 +100,9 @@ struct Engine {
   double* t;        // [C][qp]  X' a4
   double* xg;       // [C][np]  X gamma (cached between mu and the next tau2)
   double* xv;       // [C][np]  X (W + delta1)
-  double* rhs;      // [C][np]  a1 - a3, then L^-1 rhs, then a4 (in place)
-  double* G;        // [C][np*np] col-major, lower triangle used
-  double* dinv;     // [C][np]  reciprocal diagonal of the Cholesky factor
+  double* rhs;      // [C][np]  a1 - a3, then L^-1 rhs, then a4 (in place); q-form: (y - mu - X W)/tau2
+  double* G;        // [C][gdim*gdim] col-major, lower triangle used
+  double* dinv;     // [C][gdim]  reciprocal diagonal of the Cholesky factor
   double* partials; // [C][nparts][2*MAX_R+1]  block partial sums: A_r, B_r (lambda), sum S
   int* status;      // [C]
   long long* iter;  // device scalar: completed sweeps

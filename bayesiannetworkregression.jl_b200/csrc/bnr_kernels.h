@@ -24,8 +24,8 @@ extern thread_local long long g_launches;   // kernels launched through the wrap
 
 void launch_tau2(const Engine& e, cudaStream_t s);
 void launch_uxi(const Engine& e, cudaStream_t s);
-void launch_edge_prep(const Engine& e, int draw_v, cudaStream_t s);
-void launch_rhs(const Engine& e, cudaStream_t s);
+void launch_edge_prep(const Engine& e, int draw_v, cudaStream_t s);   // draw_v: 0 W only, 1 v = W + delta1, 2 v = z
+void launch_rhs(const Engine& e, cudaStream_t s);                     // n-form a1 - a3; q-form (y - mu - X W)/tau2
 void launch_gamma_gig(const Engine& e, int flags, cudaStream_t s);
 void launch_finish(const Engine& e, int mask, cudaStream_t s);
 void launch_init(const Engine& e, cudaStream_t s);
@@ -41,8 +41,13 @@ void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, in
 void launch_x_times(const Engine& e, int trans, const double* in, double* out, double* splitk_ws, cudaStream_t s);
 size_t x_times_workspace_doubles(const Dims& d);
 void launch_syrk_G(const Engine& e, cudaStream_t s);         // G_c = X diag(S_c) X' + I (lower tiles)
-void launch_cholesky(const Engine& e, cudaStream_t s);       // in-place lower Cholesky of every G_c
-void launch_chol_solve(const Engine& e, cudaStream_t s);     // rhs_c <- G_c^-1 rhs_c using the factor
+// in-place lower Cholesky of every G_c (gdim x gdim) with the forward solve folded in: rhs_c <- L_c^-1 rhs_c
+void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s);
+// rhs_c <- L_c^-T (rhs_c + addz_c); addz may be null
+void launch_chol_solve(const Engine& e, double* rhs, const double* addz, cudaStream_t s);
+void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s);   // X'X, once
+void launch_build_P(const Engine& e, cudaStream_t s);        // q-form: P_c = (X'X + diag(1/S_c)) / tau2_c
+int chol_max_dim();
 void linalg_setup();                                          // one-time cudaFuncSetAttribute calls
 
 }  // namespace bnr

@@ -169,7 +169,7 @@ __device__ __forceinline__ void syrk_diag_frags(const double* __restrict__ sj, c
 template <int MODE, int W>
 __device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, unsigned long long* full,
                                                unsigned long long* empty, int nk, int lk, int lr, int lane,
-                                               double* __restrict__ Cc, int np, int i0) {
+                                               double* __restrict__ Cc, int np, int i0, double diag_add) {
   constexpr int NA = 16 - W;        // fragments of column W
   double acc[17][2];
 #pragma unroll
@@ -207,8 +207,8 @@ __device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, 
     double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
     double2 v;
     if (MODE == 0) {
-      v.x = acc[t][0] + (i == j ? 1.0 : 0.0);
-      v.y = acc[t][1] + (i + 1 == j ? 1.0 : 0.0);
+      v.x = acc[t][0] + (i == j ? diag_add : 0.0);
+      v.y = acc[t][1] + (i + 1 == j ? diag_add : 0.0);
     } else {
       v = *p;
       v.x -= acc[t][0];
@@ -221,7 +221,8 @@ __device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, 
 template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
-          size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin) {
+          size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
+          double diag_add) {
   extern __shared__ __align__(16) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
@@ -293,14 +294,14 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
 
   if (diag) {
     switch (warp) {
-      case 0: syrk_diag_tile<MODE, 0>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 1: syrk_diag_tile<MODE, 1>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 2: syrk_diag_tile<MODE, 2>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 3: syrk_diag_tile<MODE, 3>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 4: syrk_diag_tile<MODE, 4>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 5: syrk_diag_tile<MODE, 5>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      case 6: syrk_diag_tile<MODE, 6>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
-      default: syrk_diag_tile<MODE, 7>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0); break;
+      case 0: syrk_diag_tile<MODE, 0>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 1: syrk_diag_tile<MODE, 1>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 2: syrk_diag_tile<MODE, 2>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 3: syrk_diag_tile<MODE, 3>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 4: syrk_diag_tile<MODE, 4>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 5: syrk_diag_tile<MODE, 5>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      case 6: syrk_diag_tile<MODE, 6>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
+      default: syrk_diag_tile<MODE, 7>(smem, full, empty, nk, lk, lr, lane, Cc, np, i0, diag_add); break;
     }
     return;
   }
@@ -353,14 +354,14 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ scale, size_t scale_stride,
-            double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk) {
-  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk, 0);
+            double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk, double diag_add) {
+  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk, 0, diag_add);
 }
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
               int nk, int origin) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin);
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -574,14 +575,17 @@ __global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t
 // grid = C, block = 256 (8 warps): warp per column group for the matvec with the rows below (coalesced, 8 columns in
 // flight per warp), then a 128 x 128 transposed triangular solve by one warp (shuffles, reciprocal diagonals).
 // ------------------------------------------------------------------------------------------------------------
-constexpr size_t TRSVB_SMEM = sizeof(double) * ((size_t)PB * PB_LD + 1024 + 2 * PB);
+static size_t trsvb_smem(int np) { return sizeof(double) * ((size_t)PB * PB_LD + np + 2 * PB); }
+constexpr int CHOL_MAX_DIM = 4096;   // largest factored dimension (shared-memory solution vector of the back solve)
 
+// addz (optional, [C][np]): added to the right-hand side before the solve - the q-form draws L' beta = w + z
 __global__ void __launch_bounds__(256) k_trsv_bwd128(const double* __restrict__ G, size_t chain_stride, int np,
-                                                     double* __restrict__ rhs, const double* __restrict__ dinv_g) {
+                                                     double* __restrict__ rhs, const double* __restrict__ dinv_g,
+                                                     const double* __restrict__ addz) {
   extern __shared__ double sm[];
   double* Ls = sm;                     // [r][c] lower block
   double* x = sm + PB * PB_LD;         // [np] solution so far (entries >= (J+1)*128 valid)
-  double* b = x + 1024;                // [128] current right-hand side
+  double* b = x + np;                  // [128] current right-hand side
   double* dinv = b + PB;               // [128]
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* Gc = G + (size_t)c * chain_stride;
@@ -612,7 +616,10 @@ __global__ void __launch_bounds__(256) k_trsv_bwd128(const double* __restrict__ 
         double v = acc[u];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) b[jj + u] = rc[J * PB + jj + u] - v;
+        if (lane == 0) {
+          const int idx = J * PB + jj + u;
+          b[jj + u] = rc[idx] + (addz ? addz[(size_t)c * np + idx] : 0.0) - v;
+        }
       }
     }
     __syncthreads();
@@ -760,7 +767,7 @@ void linalg_setup() {
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   cudaFuncSetAttribute(k_potf2_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
   cudaFuncSetAttribute(k_trsm_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
-  cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSVB_SMEM);
+  cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsvb_smem(CHOL_MAX_DIM));
 }
 
 void launch_syrk_G(const Engine& e, cudaStream_t s) {
@@ -774,35 +781,86 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
   dim3 grid(d.C, T * (T + 1) / 2);
 #endif
   ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np, d.n,
-                                                            d.qp / SY_BK);
+                                                            d.qp / SY_BK, 1.0);
   if (e.aux.G_copy) {
     dim3 g2(d.np, d.C);
     ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
   }
 }
 
-// factor every G_c in place AND forward-solve: rhs_c <- L_c^-1 rhs_c
-void launch_cholesky(const Engine& e, cudaStream_t s) {
+// ------------------------------------------------------------------------------------------------------------
+// q-form of the gamma draw: P_c = (X'X + diag(1/S_c)) / tau2_c  (q x q precision of gamma - W | rest).
+// X'X is computed once per handle with the same DMMA SYRK (operand = X stored row-major, K = np, unit scales).
+// ------------------------------------------------------------------------------------------------------------
+// XtX (lower tiles of a qp x qp column-major matrix) from XT[i * qp + j] = X(i, j) (np rows, zero padded)
+void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s) {
+  const int T = d.qp / SY_BT;
+  dim3 grid(1, T * (T + 1) / 2);
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(XT, d.qp, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0);
+}
+
+// P_c lower triangle from XtX, S_c, tau2_c; padding rows/columns get the identity so the factorisation stays PD.
+// grid = (qp/32, qp/32, C), block = (32, 8): tile (bi, bj) with bi >= bj only.
+__global__ void __launch_bounds__(256) k_build_P(Engine e) {
   const Dims& d = e.d;
-  const size_t cs = (size_t)d.np * d.np;
-  const int T = d.np / PB;
+  if (blockIdx.x < blockIdx.y) return;
+  const int c = blockIdx.z, N = d.qp;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const double it2 = 1.0 / e.tau2[c];
+  double* Gc = e.G + (size_t)c * N * N;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = blockIdx.y * 32 + threadIdx.y * 4 + jj;
+    if (i < j) continue;
+    double v;
+    if (i < d.q) {
+      v = e.XtX[(size_t)j * N + i] * it2;
+      if (i == j) v = (e.XtX[(size_t)j * N + i] + 1.0 / e.S[(size_t)c * d.qp + j]) * it2;
+    } else {
+      v = (i == j) ? 1.0 : 0.0;
+    }
+    Gc[(size_t)j * N + i] = v;
+  }
+}
+
+void launch_build_P(const Engine& e, cudaStream_t s) {
+  const Dims& d = e.d;
+  dim3 grid(d.qp / 32, d.qp / 32, d.C), block(32, 8);
+  ++g_launches; k_build_P<<<grid, block, 0, s>>>(e);
+  if (e.aux.G_copy) {
+    dim3 g2(d.qp, d.C);
+    ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.qp * d.qp, d.qp, e.aux.G_copy);
+  }
+}
+
+// factor every G_c (gdim x gdim) in place AND forward-solve: rhs_c <- L_c^-1 rhs_c
+void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s) {
+  const Dims& d = e.d;
+  const int N = d.gdim;
+  const int nvalid = d.gmode == 2 ? d.q : d.n;    // rows beyond are identity padding
+  const size_t cs = (size_t)N * N;
+  const int T = N / PB;
+  (void)nvalid;
   for (int J = 0; J < T; ++J) {
     if (J > 0) {
       dim3 g2(d.C, T - J);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, d.np, e.G, d.np, d.np, J * PB / SY_BK, J);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, N, J * PB / SY_BK, J);
     }
-    ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, d.np, J, e.rhs, e.dinv, e.status);
+    ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, rhs, e.dinv, e.status);
     if (J + 1 < T) {
       dim3 g1(T - J - 1, d.C);
-      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, d.np, J, e.dinv, e.rhs);
+      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, N, J, e.dinv, rhs);
     }
   }
 }
 
-// rhs_c <- L_c^-T rhs_c  (the forward half already happened inside launch_cholesky)
-void launch_chol_solve(const Engine& e, cudaStream_t s) {
+// rhs_c <- L_c^-T (rhs_c + addz_c)  (the forward half already happened inside launch_cholesky)
+void launch_chol_solve(const Engine& e, double* rhs, const double* addz, cudaStream_t s) {
   const Dims& d = e.d;
-  ++g_launches; k_trsv_bwd128<<<d.C, 256, TRSVB_SMEM, s>>>(e.G, (size_t)d.np * d.np, d.np, e.rhs, e.dinv);
+  const int N = d.gdim;
+  ++g_launches; k_trsv_bwd128<<<d.C, 256, trsvb_smem(N), s>>>(e.G, (size_t)N * N, N, rhs, e.dinv, addz);
 }
+
+int chol_max_dim() { return CHOL_MAX_DIM; }
 
 }  // namespace bnr

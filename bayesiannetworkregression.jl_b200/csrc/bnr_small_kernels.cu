@@ -277,17 +277,22 @@ __global__ void __launch_bounds__(PART_BLOCK) k_edge_prep(Engine e, int draw_v) 
     const InjLayout L = InjLayout::make(d.n, d.V, d.R, d.gigK);
     DrawStream st(chain_key(d, c), (uint32_t)it, SITE_GAMMA_Z1, (uint32_t)j,
                   e.inj ? e.inj + (size_t)c * e.inj_stride + L.z1 + j : nullptr, 1);
-    e.v[o] = w + sqrt(e.tau2[c] * e.S[o]) * st.normal();
+    const double z = st.normal();
+    // n-form: v = W + delta1, delta1 = sqrt(tau2 S) z1;  q-form (draw_v == 2): the raw normal, used as L' beta = w + z
+    e.v[o] = (draw_v == 2) ? z : w + sqrt(e.tau2[c] * e.S[o]) * z;
   }
 }
 
 // rhs = a1 - a3 = (y - mu - X(W + delta1))/tau - z2   (src/gibbs.jl:432-434).  grid = (ceil(np/256), C)
+// q-form: rhs = (y - mu - X W)/tau2 (xv then holds X W); X' rhs is the linear term of the q x q system.
 __global__ void __launch_bounds__(256) k_rhs(Engine e) {
   const Dims& d = e.d;
   const int c = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= d.np) return;
   double r = 0.0;
-  if (i < d.n) {
+  if (i < d.n && d.gmode == 2) {
+    r = (e.y[i] - e.mu[c] - e.xv[(size_t)c * d.np + i]) / e.tau2[c];
+  } else if (i < d.n) {
     const long long it = *e.iter + 1;
     const InjLayout L = InjLayout::make(d.n, d.V, d.R, d.gigK);
     DrawStream st(chain_key(d, c), (uint32_t)it, SITE_GAMMA_Z2, (uint32_t)i,
@@ -303,7 +308,8 @@ __global__ void __launch_bounds__(256) k_rhs(Engine e) {
 //   gamma_j = v_j + tau S_j t_j                      (src/gibbs.jl:435-436), t = X' a4
 //   S_j ~ GIG(1/2, psi = theta_prev, chi = (gamma_j - W_j)^2 / tau2)   (update_D!, src/gibbs.jl:454-458, src/gig.jl)
 //   partials: A_r = sum_j p_rj e_j/(tau2 S_j), B_r = sum_j p_rj^2/(tau2 S_j), sum S   (p_rj = u_rk u_rl, e = gamma - W)
-// flags: 1 = finish gamma, 2 = draw S.  grid = (nparts, C), block = PART_BLOCK.
+// flags: 1 = finish gamma, 2 = draw S, 4 = finish gamma in the q-form (gamma = W + beta, beta in e.t).
+// grid = (nparts, C), block = PART_BLOCK.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PART_BLOCK) k_gamma_gig(Engine e, int flags) {
   extern __shared__ double sm[];
@@ -321,7 +327,10 @@ __global__ void __launch_bounds__(PART_BLOCK) k_gamma_gig(Engine e, int flags) {
   if (j < d.q) {
     const size_t o = (size_t)c * d.qp + j;
     double g, s = e.S[o];
-    if (flags & 1) {
+    if (flags & 4) {
+      g = e.W[o] + e.t[o];
+      e.gamma[o] = g;
+    } else if (flags & 1) {
       g = e.v[o] + sqrt(tau2) * s * e.t[o];
       e.gamma[o] = g;
     } else {

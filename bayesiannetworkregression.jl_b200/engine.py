@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from .capi import lib, check, Params, VAR, COND, AUX
+from .capi import lib, check, Params, VAR, COND, AUX, GAMMA_MODE
 
 _DP = C.POINTER(C.c_double)
 
@@ -19,7 +19,7 @@ class Engine:
 
     def __init__(self, X, y, R, num_chains=2, seed=0, chain_offset=0, device=0, trace_rows=0,
                  trace_full_chains=1, trace_gamma_xi_all=True, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0,
-                 b_delta=1.0, nu=10.0, gig_inject_len=64):
+                 b_delta=1.0, nu=10.0, gig_inject_len=64, gamma_mode="auto"):
         X = np.asarray(X, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64)
         if X.ndim != 2 or y.ndim != 1 or X.shape[0] != y.shape[0]:
@@ -39,6 +39,7 @@ class Engine:
         p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         p.eta, p.zeta, p.iota, p.a_delta, p.b_delta, p.nu = eta, zeta, iota, a_delta, b_delta, float(nu)
         p.gig_inject_len = int(gig_inject_len)
+        p.gamma_mode = GAMMA_MODE[gamma_mode] if isinstance(gamma_mode, str) else int(gamma_mode)
         self.params = p
         self.device = int(device)
         self.trace_rows = int(trace_rows)
@@ -64,6 +65,13 @@ class Engine:
 
     def __exit__(self, *a):
         self.close()
+
+    @property
+    def gamma_mode(self):
+        """"nform" (the reference's n x n Bhattacharya draw) or "qform" (q x q precision Cholesky)."""
+        v = C.c_int32()
+        check(self._L.bnr_gamma_mode(self._h, C.byref(v)))
+        return {1: "nform", 2: "qform"}[int(v.value)]
 
     # -- sampling --------------------------------------------------------------------------------------
     def init_state(self):
@@ -219,6 +227,8 @@ class Engine:
 
     def get_aux(self, chain, name):
         R, V, q, n = self.R, self.V, self.q, self.n
+        if self.gamma_mode == "qform":
+            n = q          # G / G_chol are q x q (the precision P), rhs / a4 hold beta = gamma - W
         size = {"tau2_params": 2, "sigma_inv": V * R * R, "sigma_chol": V * R * R, "mu_t": V * R, "log_odds": V,
                 "W": q, "G": n * n, "G_chol": n * n, "rhs": n, "a4": n, "chi": q, "theta_params": 2,
                 "delta_params": 2, "m_params": 1 + 2 * R * R, "mu_params": 2, "lambda_logw": 3 * R,

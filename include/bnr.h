@@ -73,10 +73,11 @@ enum {
   BNR_AUX_MU_T = 3,          /* [V*R]      per node conditional mean of u_k                        */
   BNR_AUX_LOG_ODDS = 4,      /* [V]        log(w_bot / w_top); w = 1/(1+exp(.))                    */
   BNR_AUX_W = 5,             /* [q]        W = lower_triangle(u' Lambda u)                         */
-  BNR_AUX_G = 6,             /* [n*n]      X D X' + I, col-major (symmetric, both triangles filled) */
-  BNR_AUX_G_CHOL = 7,        /* [n*n]      its lower Cholesky factor (strict upper = 0)            */
+  BNR_AUX_G = 6,             /* [n*n]      X D X' + I, col-major (symmetric, both triangles filled);
+                                           QFORM: [q*q] the precision P = (X'X + D^-1)/tau2         */
+  BNR_AUX_G_CHOL = 7,        /* [n*n]      its lower Cholesky factor (strict upper = 0); QFORM: [q*q] */
   BNR_AUX_RHS = 8,           /* [n]        a1 - a3                                                  */
-  BNR_AUX_A4 = 9,            /* [n]        (X D X' + I)^-1 (a1 - a3)                                */
+  BNR_AUX_A4 = 9,            /* [n]        (X D X' + I)^-1 (a1 - a3); QFORM: [q] beta = gamma - W  */
   BNR_AUX_CHI = 10,          /* [q]        GIG chi_j = (gamma_j - W_j)^2 / tau2                     */
   BNR_AUX_THETA_PARAMS = 11, /* [2]        shape, scale                                             */
   BNR_AUX_DELTA_PARAMS = 12, /* [2]        a, b                                                     */
@@ -114,8 +115,19 @@ typedef struct bnr_params {
   uint64_t seed;
   double eta, zeta, iota, a_delta, b_delta, nu;   /* Fit! hyper-parameters (src/gibbs.jl:725) */
   int32_t gig_inject_len;    /* K: injected uniforms per edge in injection mode (default 64) */
-  int32_t reserved;
+  int32_t gamma_mode;        /* BNR_GAMMA_AUTO (cost model) | BNR_GAMMA_NFORM | BNR_GAMMA_QFORM              */
 } bnr_params;
+
+/* Formulation of the gamma draw (update_gamma!, src/gibbs.jl:420-438).  Both sample the same conditional
+ * N(W + m, P^-1), P = (X'X + D^-1)/tau2:
+ *  NFORM  the reference's literal Bhattacharya draw through the n x n system X D X' + I (n^2 q + n^3/3 flops);
+ *         consumes z1 (q normals) and z2 (n normals).
+ *  QFORM  factors the q x q precision P = L L' directly (q^3/3 flops): L w = X'(y - mu - X W)/tau2,
+ *         L' beta = w + z, gamma = W + beta; consumes z (q normals, the z1 site).
+ *  AUTO   picks the cheaper one: QFORM iff q^3/3 + 4 q^2 < n^2 q + n^3/3 (roughly n > 0.53 q). */
+#define BNR_GAMMA_AUTO 0
+#define BNR_GAMMA_NFORM 1
+#define BNR_GAMMA_QFORM 2
 
 #define BNR_MAX_R 16
 
@@ -170,6 +182,8 @@ int bnr_status(bnr_handle* h, int32_t* status_per_chain);
 
 /* copy the moments buffer into caller-owned DEVICE memory (e.g. the input of an NCCL all-gather) */
 int bnr_export_moments(bnr_handle* h, double* dev_dst);
+/* which gamma formulation the handle runs (BNR_GAMMA_NFORM / BNR_GAMMA_QFORM; AUTO is resolved at create) */
+int bnr_gamma_mode(bnr_handle* h, int32_t* mode);
 /* number of CUDA kernels launched by bnr_run on this handle so far (graph replays counted per kernel node) */
 int bnr_launch_count(bnr_handle* h, int64_t* kernels);
 /* one eager sweep with CUDA events between phases; ms[8] = tau2, (u,xi), gamma prep, SYRK, Cholesky, solves,

@@ -201,6 +201,21 @@ def update_gamma(X, y, tau2, u_new, lam_prev, S_prev, mu_prev, z1, z2):
     return dict(W=W, G=G, a1=a1, a3=a3, a4=a4, gamma=gamma, delta1=d1)
 
 
+def update_gamma_qform(X, y, tau2, u_new, lam_prev, S_prev, mu_prev, z):
+    """The same conditional as update_gamma (src/gibbs.jl:420-438: gamma | rest ~ N(W + m, P^-1)) drawn through
+    the q x q precision: P = (X'X + D^-1)/tau2 = L L', L w = X'(y - mu - XW)/tau2, L' beta = w + z, gamma = W + beta.
+    The reference never forms P; this restates BASELINE.json's q-form so the CUDA q-form has a checker.
+    Equivalence with the reference's draw is in law (mean m and covariance P^-1, see gamma_conditional_moments),
+    not per injected normal."""
+    W = W_of(u_new, lam_prev)
+    P = (X.T @ X + np.diag(1.0 / S_prev)) / tau2
+    L = np.linalg.cholesky(P)
+    b = X.T @ ((y - mu_prev - X @ W) / tau2)
+    w = np.linalg.solve(L, b)
+    beta = np.linalg.solve(L.T, w + z)
+    return dict(W=W, P=P, L=L, b=b, w=w, beta=beta, mean=W + np.linalg.solve(L.T, w), gamma=W + beta)
+
+
 def gamma_conditional_moments(X, y, tau2, W, S_prev, mu_prev):
     """Mean and precision of gamma | rest: P = (X'X + D^-1)/tau2, m = W + P^-1 X'(y-mu-XW)/tau2.
     Used by the distributional tests."""
@@ -532,8 +547,9 @@ def draw_layout(n, V, R, K_gig):
     return off
 
 
-def gibbs_sweep(state, X, y, V, R, hyper, inj, K_gig, literal=True):
+def gibbs_sweep(state, X, y, V, R, hyper, inj, K_gig, literal=True, gamma_form="n"):
     """One gibbs_sample! with every basic variate read from `inj` (layout: draw_layout).
+    gamma_form "n" = the reference's n x n draw (z1, z2), "q" = the q x q precision draw (z1 only).
     Returns (new_state, aux)."""
     n = X.shape[0]
     lay = draw_layout(n, V, R, K_gig)
@@ -552,8 +568,11 @@ def gibbs_sweep(state, X, y, V, R, hyper, inj, K_gig, literal=True):
                      state["M"], uz[:, 0], uz[:, 1:], literal)
     new["u"], new["xi"] = ux["u"], ux["xi"]
     aux["uxi"] = ux
-    g = update_gamma(X, y, new["tau2"], new["u"], state["lam"], state["S"], state["mu"],
-                     seg("gamma_z1"), seg("gamma_z2"))
+    if gamma_form == "q":
+        g = update_gamma_qform(X, y, new["tau2"], new["u"], state["lam"], state["S"], state["mu"], seg("gamma_z1"))
+    else:
+        g = update_gamma(X, y, new["tau2"], new["u"], state["lam"], state["S"], state["mu"],
+                         seg("gamma_z1"), seg("gamma_z2"))
     new["gamma"] = g["gamma"]
     aux["gamma"] = g
     q = V * (V + 1) // 2

@@ -249,3 +249,71 @@ def test_full_size_properties(bnr):
         np.testing.assert_allclose(st["pi"].sum(axis=1), 1.0, rtol=1e-12)
         ev = np.linalg.eigvalsh(st["M"])
         assert ev.min() > 0
+
+
+def test_qform_and_nform_sample_the_same_posterior(bnr, golden):
+    """The q x q precision draw and the reference's n x n Bhattacharya draw are two samplers of one conditional:
+    full Gibbs runs under either formulation must agree on every posterior mean within 4 Monte-Carlo s.e."""
+    X, y = golden["test1.X"], golden["test1.y"]
+    nburn, nsamp, C = 500, 800, 12
+    out = {}
+    for mode in ("nform", "qform"):
+        with bnr.Engine(X, y, 5, num_chains=C, seed=31 if mode == "nform" else 32, trace_rows=nburn + nsamp + 1,
+                        trace_full_chains=C, gamma_mode=mode) as eng:
+            assert eng.gamma_mode == mode
+            eng.init_state()
+            eng.run(nburn + nsamp)
+            out[mode] = {k: np.concatenate([eng.get_trace(c, k, nburn + 1, nburn + nsamp + 1).reshape(nsamp, -1)
+                                            for c in range(C)]) for k in ("gamma", "xi", "tau2", "mu", "theta", "Delta")}
+            assert not (eng.status() & ~1).any()
+    failures = []
+    for k in ("tau2", "mu", "theta", "Delta", "gamma", "xi"):
+        a, b = out["nform"][k], out["qform"][k]
+        se = np.sqrt(_batch_se(a, 24) ** 2 + _batch_se(b, 24) ** 2)
+        z = np.abs(a.mean(axis=0) - b.mean(axis=0)) / np.maximum(se, 1e-12)
+        frac = float(np.mean(z > 4.0))
+        if frac > 0.03:
+            failures.append((k, frac, float(z.max())))
+    assert not failures, failures
+
+
+def test_qform_full_size_properties(bnr):
+    """BASELINE config 2 shape (V=30, q=465, n=500, R=7), where the cost model picks the q x q form:
+    L L' = P = (X'X + D^-1)/tau2 and P beta = X'(y - mu - XW)/tau2 + L z at full size."""
+    V, R, n, C = 30, 7, 500, 3
+    rng = np.random.default_rng(1)
+    q = V * (V + 1) // 2
+    X = (rng.random((n, q)) < 0.5) * (0.13 + rng.gamma(1.2, 0.2, size=(n, q)))
+    X[:, np.cumsum([0] + [V - k for k in range(V - 1)])] = 0.0        # zero diagonal columns, like the shipped example
+    y = 55 + X[:, :20].sum(axis=1) + rng.normal(0, 10, size=n)
+    with bnr.Engine(X, y, R, num_chains=C, seed=1) as eng:
+        assert eng.gamma_mode == "qform"
+        eng.init_state()
+        eng.run(2)
+        eng.enable_aux(True)
+        S_old = eng.get_state(1, "S")[:, 0].copy()
+        mu_old = float(eng.get_state(1, "mu")[0, 0])
+        eng.step("tau2"); eng.step("u_xi"); eng.step("gamma")
+        tau2 = float(eng.get_state(1, "tau2")[0, 0])
+        P = eng.get_aux(1, "G").reshape(q, q).T
+        L = eng.get_aux(1, "G_chol").reshape(q, q).T
+        beta = eng.get_aux(1, "a4")
+        W = eng.get_aux(1, "W")
+        want = (X.T @ X + np.diag(1.0 / S_old)) / tau2
+        scale = np.abs(want).max()
+        assert np.abs(P - want).max() <= 1e-13 * scale
+        assert np.abs(L @ L.T - want).max() <= 1e-12 * scale
+        b = X.T @ ((y - mu_old - X @ W) / tau2)
+        zrec = np.linalg.solve(L, want @ beta - b)            # P beta - b = L z
+        for j in (0, 17, q - 1):                              # site GAMMA_Z1 = 3 (bnr_rng.cuh), sweep 3
+            z = eng.rng_stream(1, 3, 3, j, "normal", 1)[0]
+            assert abs(zrec[j] - z) <= 1e-6, (j, zrec[j], z)
+        np.testing.assert_allclose(eng.get_state(1, "gamma")[:, 0], W + beta, rtol=1e-14)
+        for cond in ("D", "theta", "Delta", "M", "mu", "lam", "pi"):
+            eng.step(cond)
+        eng.finish_sweep()
+        eng.enable_aux(False)
+        eng.run(5)
+        st = eng.get_state_dict(2)
+        assert eng.iteration == 8 and not (eng.status() & ~1).any()
+        assert np.isfinite(st["gamma"]).all() and (st["S"] > 0).all() and st["tau2"] > 0

@@ -64,7 +64,7 @@ def close(a, b, rtol=RTOL, atol=0.0, msg=""):
 def small(bnr):
     V, R, n, C, K = 7, 4, 23, 3, 64
     X, y = make_problem(11, V, R, n)
-    eng = bnr.Engine(X, y, R, num_chains=C, seed=5, gig_inject_len=K)
+    eng = bnr.Engine(X, y, R, num_chains=C, seed=5, gig_inject_len=K, gamma_mode="nform")
     eng.enable_aux(True)
     rng = np.random.default_rng(2)
     states = [random_state(rng, V, R) for _ in range(C)]
@@ -158,6 +158,56 @@ def test_gamma(small):
     assert not (eng.status() & 4).any()
 
 
+def test_gamma_qform(bnr):
+    """q x q precision form (BASELINE north_star): P, chol(P), conditional mean and the draw given injected z."""
+    V, R, n, C, K = 7, 4, 40, 3, 64
+    q = V * (V + 1) // 2
+    X, y = make_problem(21, V, R, n)
+    rng = np.random.default_rng(8)
+    states = [random_state(rng, V, R) for _ in range(C)]
+    injs = [sweep_injection(rng, n, V, R, K) for _ in range(C)]
+    inj, lay = np.stack([i[0] for i in injs]), injs[0][1]
+    with bnr.Engine(X, y, R, num_chains=C, seed=5, gig_inject_len=K, gamma_mode="qform") as eng:
+        assert eng.gamma_mode == "qform"
+        eng.enable_aux(True)
+        for c, st in enumerate(states):
+            eng.set_state_dict(c, st)
+        eng.set_injection(inj)
+        eng.step("gamma")
+        for c, st in enumerate(states):
+            o, s = lay["gamma_z1"]
+            want = O.update_gamma_qform(X, y, st["tau2"], st["u"], st["lam"], st["S"], st["mu"], inj[c, o:o + s])
+            cond = np.linalg.cond(want["P"])
+            P = eng.get_aux(c, "G").reshape(q, q).T
+            close(P, want["P"], atol=1e-13 * np.abs(want["P"]).max(), msg="P")
+            Lg = eng.get_aux(c, "G_chol").reshape(q, q).T
+            close(Lg, want["L"], rtol=RTOL * cond, atol=1e-13 * cond, msg="chol(P)")
+            close(eng.get_aux(c, "a4"), want["beta"], rtol=RTOL * cond, atol=1e-13 * cond, msg="beta")
+            close(eng.get_state(c, "gamma")[:, 0], want["gamma"], rtol=RTOL * cond, atol=1e-13 * cond, msg="gamma")
+        assert not (eng.status() & 4).any()
+        # z = 0 gives the conditional mean, which is also the reference's Bhattacharya draw with z1 = z2 = 0
+        inj0 = inj.copy()
+        o, s = lay["gamma_z1"]; inj0[:, o:o + s] = 0.0
+        for c, st in enumerate(states):
+            eng.set_state_dict(c, st)
+        eng.set_injection(inj0)
+        eng.step("gamma")
+        for c, st in enumerate(states):
+            ref = O.update_gamma(X, y, st["tau2"], st["u"], st["lam"], st["S"], st["mu"], np.zeros(q), np.zeros(n))
+            cond = np.linalg.cond(ref["G"])
+            close(eng.get_state(c, "gamma")[:, 0], ref["gamma"], rtol=max(1e-9, RTOL * cond), atol=1e-12 * cond, msg="mean")
+
+
+def test_gamma_mode_cost_model(bnr):
+    """AUTO resolves by the SURVEY 8(d) flop model: q-form iff q^3/3 + 4q^2 < n^2 q + n^3/3."""
+    for V, n, want in ((6, 40, "qform"), (6, 8, "nform"), (12, 30, "nform"), (12, 60, "qform")):
+        q = V * (V + 1) // 2
+        X, y = make_problem(1, V, 3, n)
+        with bnr.Engine(X, y, 3, num_chains=1, seed=1) as eng:
+            assert (q ** 3 / 3 + 4 * q * q < n * n * q + n ** 3 / 3) == (want == "qform")
+            assert eng.gamma_mode == want, (V, n)
+
+
 def test_D_gig(small):
     p = small
     # cover all three GIG branches: scale some residuals down / up
@@ -236,14 +286,16 @@ def test_lambda_pi(small):
         close(eng.get_state(c, "pi"), want["pi"])
 
 
-@pytest.mark.parametrize("V,R,n,dense", [(7, 4, 23, True), (12, 5, 150, False), (20, 7, 300, True)])
-def test_full_sweeps_injected(bnr, V, R, n, dense):
+@pytest.mark.parametrize("V,R,n,dense,mode", [(7, 4, 23, True, "nform"), (12, 5, 150, False, "nform"),
+                                              (20, 7, 300, True, "nform"), (7, 4, 23, True, "qform"),
+                                              (18, 5, 150, False, "qform"), (22, 7, 300, True, "qform")])
+def test_full_sweeps_injected(bnr, V, R, n, dense, mode):
     """bnr_run (production schedule, fused kernels) == oracle gibbs_sweep for consecutive sweeps; the larger
     cases span several 128-row tiles and 64-column Cholesky panels."""
     C, K = 2, 64
     X, y = make_problem(V * 100 + n, V, R, n, dense)
     rng = np.random.default_rng(V)
-    with bnr.Engine(X, y, R, num_chains=C, seed=1, gig_inject_len=K, trace_rows=4) as eng:
+    with bnr.Engine(X, y, R, num_chains=C, seed=1, gig_inject_len=K, trace_rows=4, gamma_mode=mode) as eng:
         init = np.stack([_init_injection(rng, V, R) for _ in range(C)])
         eng.set_injection(init)
         eng.init_state()
@@ -257,8 +309,9 @@ def test_full_sweeps_injected(bnr, V, R, n, dense):
             eng.set_injection(inj)
             eng.run(1)
             for c in range(C):
-                new, aux = O.gibbs_sweep(sts[c], X, y, V, R, O.DEFAULT_HYPER, inj[c], K, literal=False)
-                cond = np.linalg.cond(aux["gamma"]["G"])
+                new, aux = O.gibbs_sweep(sts[c], X, y, V, R, O.DEFAULT_HYPER, inj[c], K, literal=False,
+                                         gamma_form="q" if mode == "qform" else "n")
+                cond = np.linalg.cond(aux["gamma"]["P" if mode == "qform" else "G"])
                 got = eng.get_state_dict(c)
                 tol = max(1e-9, RTOL * cond)
                 for k in ("tau2", "xi", "lam"):

@@ -247,3 +247,32 @@ def test_sweep_from_injected_draws_is_self_consistent():
             np.testing.assert_allclose(a[key], b[key], rtol=1e-9, atol=1e-12, err_msg=key)
         st = a
     assert np.all(st["S"] > 0) and st["tau2"] > 0
+
+
+def test_qform_gamma_draw_has_the_reference_conditional_law():
+    """The q x q precision draw (oracle.update_gamma_qform, BASELINE's formulation) and the reference's n x n
+    Bhattacharya draw (update_gamma, src/gibbs.jl:420-438) are the same Gaussian: equal mean (all normals 0)
+    and equal covariance (the n-form is linear in (z1, z2): gamma = mean + A1 z1 + A2 z2, A1 A1' + A2 A2' = P^-1)."""
+    rng = np.random.default_rng(5)
+    V, R, n = 5, 3, 9
+    q = V * (V + 1) // 2
+    X = rng.normal(size=(n, q))
+    y = rng.normal(size=n) + X[:, 0]
+    u = rng.normal(size=(R, V)); lam = np.array([1.0, 0.0, -1.0]); S = rng.gamma(1.0, size=q) + 0.05
+    tau2, mu = 1.7, 0.3
+    zq, zn = np.zeros(q), np.zeros(n)
+    a = O.update_gamma(X, y, tau2, u, lam, S, mu, zq, zn)
+    b = O.update_gamma_qform(X, y, tau2, u, lam, S, mu, zq)
+    np.testing.assert_allclose(a["gamma"], b["gamma"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(b["mean"], b["gamma"], rtol=0, atol=0)
+    A1 = np.stack([O.update_gamma(X, y, tau2, u, lam, S, mu, np.eye(q)[j], zn)["gamma"] - a["gamma"] for j in range(q)], axis=1)
+    A2 = np.stack([O.update_gamma(X, y, tau2, u, lam, S, mu, zq, np.eye(n)[i])["gamma"] - a["gamma"] for i in range(n)], axis=1)
+    cov_n = A1 @ A1.T + A2 @ A2.T
+    cov_q = np.linalg.inv(b["P"])
+    np.testing.assert_allclose(cov_n, cov_q, rtol=1e-8, atol=1e-10)
+    # and the q-form draw itself is mean + L^-T z
+    z = rng.normal(size=q)
+    c = O.update_gamma_qform(X, y, tau2, u, lam, S, mu, z)
+    np.testing.assert_allclose(c["gamma"], b["gamma"] + np.linalg.solve(b["L"].T, z), rtol=1e-10, atol=1e-12)
+    m, P = O.gamma_conditional_moments(X, y, tau2, b["W"], S, mu)
+    np.testing.assert_allclose(m, b["mean"], rtol=1e-9, atol=1e-11)
