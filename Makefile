@@ -3,7 +3,7 @@ NVCC ?= nvcc
 PKG := bayesiannetworkregression.jl_b200
 CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
-OBJS := $(CSRC)/bnr_small_kernels.o $(CSRC)/bnr_linalg.o $(CSRC)/bnr_api.o
+OBJS := $(CSRC)/bnr_small_kernels.o $(CSRC)/bnr_linalg.o $(CSRC)/bnr_diagnostics.o $(CSRC)/bnr_api.o
 HDRS := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/bnr.h
 
 all: $(PKG)/libbnr.so

@@ -61,6 +61,12 @@ PROTOTYPES = {
     "bnr_get_trace": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _DP]),
     "bnr_status": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_export_moments": (C.c_int, [_H, C.c_void_p]),
+    "bnr_summary": (C.c_int, [_H, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _DP, _DP, _DP, _DP]),
+    "bnr_ess": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32, _DP, _DP]),
+    "bnr_ess_accumulate": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32]),
+    "bnr_ess_device": (C.c_int, [_H, C.POINTER(C.c_void_p), _I64P, C.POINTER(C.c_void_p), _I64P, C.POINTER(C.c_int32)]),
+    "bnr_ess_from_stats": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int64, C.c_int32, _DP, _DP]),
     "bnr_gamma_mode": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_launch_count": (C.c_int, [_H, _I64P]),
     "bnr_profile_sweep": (C.c_int, [_H, C.POINTER(C.c_float)]),

@@ -53,6 +53,12 @@ struct bnr_handle {
   double* d_rhat = nullptr;      // [V+q]
   double* d_tmp = nullptr;       // staging for get/set (max var size / trace chunk)
   size_t tmp_doubles = 0;
+  // ESS statistics of the last bnr_ess_accumulate
+  double* d_acov = nullptr;      // [max_lag + 1][V + q]  sum over local chains of the biased autocovariances
+  double* d_cmean = nullptr;     // [C][V + q]
+  int ess_lag = -1;
+  long long ess_rows = 0;
+  size_t acov_cap = 0;
 };
 
 template <typename T>
@@ -802,6 +808,118 @@ extern "C" int bnr_rng_gamma(bnr_handle* h, int32_t chain, int64_t iteration, in
                              double shape, int32_t count, double* out) {
   if (!(shape > 0.0)) return fail(BNR_EINVAL, "shape must be positive");
   return rng_dump(h, chain, iteration, site, element, 2, shape, count, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Summary on the device (src/gibbs.jl:1214-1250): mean and the two order statistics per edge, mean xi per node
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int bnr_summary(bnr_handle* h, int32_t chain, int64_t first_row, int64_t nrows, int64_t rank_lo,
+                           int64_t rank_hi, double* gamma_mean, double* gamma_lo, double* gamma_hi, double* xi_mean) {
+  if (!h || chain < 0 || chain >= h->e.d.C || first_row < 0 || nrows < 1)
+    return fail(BNR_EINVAL, "bad arguments");
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
+  if (rank_lo < 1 || rank_hi < 1 || rank_lo > nrows || rank_hi > nrows)
+    return fail(BNR_EINVAL, "order-statistic ranks must lie in 1..nrows (the reference raises a BoundsError)");
+  CK(cudaSetDevice(h->p.device));
+  const double* rows = nullptr;
+  size_t rowlen = 0;
+  int off_g = 0, off_x = 0;
+  if (chain < e.trace_full_chains && e.tr_full) {
+    rowlen = e.rowlen_full;
+    rows = e.tr_full + (size_t)chain * e.trace_rows * rowlen;
+    off_g = row_offset(d, BNR_VAR_GAMMA); off_x = row_offset(d, BNR_VAR_XI);
+  } else if (e.tr_gx) {
+    rowlen = d.V + d.q;
+    rows = e.tr_gx + (size_t)chain * e.trace_rows * rowlen;
+    off_g = d.V; off_x = 0;
+  } else {
+    return fail(BNR_ESTATE, "gamma/xi of this chain are not traced");
+  }
+  if ((size_t)(3 * d.q + d.V) > h->tmp_doubles) return fail(BNR_EINVAL, "staging buffer too small");
+  double* o = h->d_tmp;
+  launch_summary_select(rows, rowlen, off_g, d.q, first_row, nrows, rank_lo, rank_hi, o, o + d.q, o + 2 * d.q, h->stream);
+  launch_summary_select(rows, rowlen, off_x, d.V, first_row, nrows, 1, 1, o + 3 * d.q, nullptr, nullptr, h->stream);
+  std::vector<double> host((size_t)3 * d.q + d.V);
+  CK(cudaMemcpyAsync(host.data(), o, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (gamma_mean) memcpy(gamma_mean, host.data(), sizeof(double) * d.q);
+  if (gamma_lo) memcpy(gamma_lo, host.data() + d.q, sizeof(double) * d.q);
+  if (gamma_hi) memcpy(gamma_hi, host.data() + 2 * d.q, sizeof(double) * d.q);
+  if (xi_mean) memcpy(xi_mean, host.data() + 3 * d.q, sizeof(double) * d.V);
+  return BNR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Effective sample size of xi / gamma over rows [first_row, first_row + nrows) of every chain's trace
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag) {
+  if (!h || first_row < 0 || nrows < 4 || max_lag < 1) return fail(BNR_EINVAL, "bad arguments (need nrows >= 4, max_lag >= 1)");
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  if (!e.tr_gx) return fail(BNR_ESTATE, "gamma/xi traces are not recorded (trace_gamma_xi_all = 0)");
+  if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
+  if (max_lag > nrows - 1) max_lag = (int32_t)(nrows - 1);
+  if (!(max_lag & 1)) max_lag -= 1;                  // Geyer pairs (2t, 2t+1): keep the last lag odd
+  if (max_lag < 1) max_lag = 1;
+  CK(cudaSetDevice(h->p.device));
+  const int P = d.V + d.q;
+  const size_t need = (size_t)(max_lag + 1) * P;
+  if (need > h->acov_cap) {
+    double* pnew = nullptr;
+    CK(cudaMalloc((void**)&pnew, need * sizeof(double)));
+    h->allocs.push_back(pnew);
+    h->d_acov = pnew;
+    h->acov_cap = need;
+  }
+  if (!h->d_cmean) DA(h->d_cmean, (size_t)d.C * P);
+  launch_chain_mean(e.tr_gx, e.trace_rows, P, d.C, first_row, nrows, h->d_cmean, h->stream);
+  launch_acov_sum(e.tr_gx, e.trace_rows, P, d.C, first_row, nrows, max_lag, h->d_cmean, h->d_acov, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->ess_lag = max_lag;
+  h->ess_rows = nrows;
+  return BNR_OK;
+}
+
+extern "C" int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov, double** chain_mean,
+                              int64_t* n_mean, int32_t* max_lag) {
+  if (!h || !acov_sum || !n_acov || !chain_mean || !n_mean || !max_lag) return fail(BNR_EINVAL, "null argument");
+  if (h->ess_lag < 0) return fail(BNR_ESTATE, "call bnr_ess_accumulate first");
+  const int P = h->e.d.V + h->e.d.q;
+  *acov_sum = h->d_acov; *n_acov = (int64_t)(h->ess_lag + 1) * P;
+  *chain_mean = h->d_cmean; *n_mean = (int64_t)h->e.d.C * P;
+  *max_lag = h->ess_lag;
+  return BNR_OK;
+}
+
+extern "C" int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts,
+                                  const double* dev_chain_means, int32_t total_chains, int32_t V, int32_t q,
+                                  int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma) {
+  if (!dev_acov_parts || !dev_chain_means || nparts < 1 || total_chains < 1 || nrows < 4 || max_lag < 1)
+    return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(device));
+  const int P = V + q;
+  double* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_out, sizeof(double) * P));
+  launch_ess_finish(dev_acov_parts, nparts, dev_chain_means, total_chains, P, nrows, max_lag, d_out, nullptr, 0);
+  std::vector<double> host(P);
+  cudaError_t err = cudaMemcpy(host.data(), d_out, sizeof(double) * P, cudaMemcpyDeviceToHost);
+  cudaFree(d_out);
+  CK(err);
+  if (ess_xi) memcpy(ess_xi, host.data(), sizeof(double) * V);
+  if (ess_gamma) memcpy(ess_gamma, host.data() + V, sizeof(double) * q);
+  return BNR_OK;
+}
+
+extern "C" int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag, double* ess_xi,
+                       double* ess_gamma) {
+  int r = bnr_ess_accumulate(h, first_row, nrows, max_lag);
+  if (r) return r;
+  const Dims& d = h->e.d;
+  return bnr_ess_from_stats(h->p.device, h->d_acov, 1, h->d_cmean, d.C, d.V, d.q, nrows, h->ess_lag, ess_xi, ess_gamma);
 }
 
 extern "C" int bnr_gamma_mode(bnr_handle* h, int32_t* mode) {

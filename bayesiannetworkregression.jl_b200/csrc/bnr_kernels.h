@@ -50,4 +50,15 @@ void launch_build_P(const Engine& e, cudaStream_t s);        // q-form: P_c = (X
 int chol_max_dim();
 void linalg_setup();                                          // one-time cudaFuncSetAttribute calls
 
+// posterior diagnostics on the device (bnr_diagnostics.cu)
+void launch_summary_select(const double* rows, size_t rowlen, int off, int nelem, long long first, long long count,
+                           long long rank_lo, long long rank_hi, double* mean_out, double* lo_out, double* hi_out,
+                           cudaStream_t s);
+void launch_chain_mean(const double* tr, long long trace_rows, int P, int C, long long first, long long N,
+                       double* cmean, cudaStream_t s);
+void launch_acov_sum(const double* tr, long long trace_rows, int P, int C, long long first, long long N, int L,
+                     const double* cmean, double* acov, cudaStream_t s);
+void launch_ess_finish(const double* acov_parts, int nparts, const double* cmeans, int chains, int P, long long N,
+                       int L, double* ess, double* lag_used, cudaStream_t s);
+
 }  // namespace bnr

@@ -141,6 +141,37 @@ class Engine:
                                             int(half_len), _dp(rx), _dp(rg)))
         return rx, rg
 
+    def summary(self, chain, first_row, nrows, rank_lo, rank_hi):
+        """Device Summary statistics of one chain: (mean gamma, sort(gamma)[rank_lo], sort(gamma)[rank_hi], mean xi);
+        ranks are 1-based like the reference's lw / hi (src/gibbs.jl:1221-1236)."""
+        gm, gl, gh, xm = np.empty(self.q), np.empty(self.q), np.empty(self.q), np.empty(self.V)
+        check(self._L.bnr_summary(self._h, int(chain), int(first_row), int(nrows), int(rank_lo), int(rank_hi),
+                                  _dp(gm), _dp(gl), _dp(gh), _dp(xm)))
+        return gm, gl, gh, xm
+
+    def ess(self, first_row, nrows, max_lag=255):
+        """(ESS of xi, ESS of gamma) over the rows of all local chains (multi-chain Geyer estimator)."""
+        ex, eg = np.empty(self.V), np.empty(self.q)
+        check(self._L.bnr_ess(self._h, int(first_row), int(nrows), int(max_lag), _dp(ex), _dp(eg)))
+        return ex, eg
+
+    def ess_accumulate(self, first_row, nrows, max_lag=255):
+        check(self._L.bnr_ess_accumulate(self._h, int(first_row), int(nrows), int(max_lag)))
+
+    def ess_device(self):
+        """((acov ptr, count), (chain-mean ptr, count), max_lag) device buffers of the last ess_accumulate."""
+        pa, pm = C.c_void_p(), C.c_void_p()
+        na, nm = C.c_int64(), C.c_int64()
+        lag = C.c_int32()
+        check(self._L.bnr_ess_device(self._h, C.byref(pa), C.byref(na), C.byref(pm), C.byref(nm), C.byref(lag)))
+        return (pa.value, int(na.value)), (pm.value, int(nm.value)), int(lag.value)
+
+    def ess_from_stats(self, acov_ptr, nparts, means_ptr, total_chains, nrows, max_lag):
+        ex, eg = np.empty(self.V), np.empty(self.q)
+        check(self._L.bnr_ess_from_stats(self.device, C.c_void_p(acov_ptr), int(nparts), C.c_void_p(means_ptr),
+                                         int(total_chains), self.V, self.q, int(nrows), int(max_lag), _dp(ex), _dp(eg)))
+        return ex, eg
+
     def export_moments(self, dev_ptr):
         check(self._L.bnr_export_moments(self._h, C.c_void_p(dev_ptr)))
 

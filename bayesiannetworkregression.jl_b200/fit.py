@@ -158,6 +158,23 @@ def _fetch_state(eng, rows, what):
     return st
 
 
+def _summary_ranks(nsamp, interval):
+    """lw / hi of src/gibbs.jl:1221-1223 (Julia round = ties to even, 1-based indices)."""
+    lower = (100 - interval) / 200.0
+    return _jround(nsamp * lower), _jround(nsamp * (1.0 - lower))
+
+
+def _device_summary(eng, nb, nsamp, interval=95):
+    """Summary statistics of chain 1 computed on the GPU from the device traces (bnr_summary): no nsamp x q
+    device-to-host copy and no host sort.  None when nsamp is too small for the interval (the reference raises
+    a BoundsError inside Summary, not inside Fit!)."""
+    lw, hi = _summary_ranks(nsamp, interval)
+    if lw < 1 or hi > nsamp:
+        return None
+    gm, gl, gh, xm = eng.summary(0, nb, nsamp, lw, hi)
+    return dict(interval=interval, mean=gm, lower=gl, upper=gh, xi_mean=xm, V=eng.V, q=eng.q)
+
+
 def _max(a):
     return np.max(a) if len(a) else -np.inf   # NaN propagates like Julia's max(...)
 
@@ -257,7 +274,8 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
         if engine_hook is not None:
             engine_hook(eng)
         state = _fetch_state(eng, tot_save, return_state)
-        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed)
+        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
+                     device_summary=_device_summary(eng, nb, nsamp))
         return Results(state, rx, rg, nb, nsamp, extra)
     finally:
         eng.close()
@@ -307,7 +325,8 @@ def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, 
                 print("%d samples generated. Max PSRF XI: %.3f. Max PSRF Gamma: %.3f" %
                       (tot_generated, _max(rx), _max(rg)))
         state = _fetch_state(eng, tot_sze, return_state)
-        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed)
+        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
+                     device_summary=_device_summary(eng, nb, nsamp))
         return Results(state, rx, rg, nb, nsamp, extra)
     finally:
         eng.close()
@@ -317,19 +336,27 @@ def Summary(results, interval=95, digits=3):
     """src/gibbs.jl:1214-1250: per-edge posterior mean and order-statistic credible bounds, per-node mean xi."""
     nburn, nsamp = results.burn_in, results.sampled
     total = nburn + nsamp
-    g = np.asarray(results.state["gamma"])[nburn:total, :, 0]
-    x = np.asarray(results.state["xi"])[nburn:total, :, 0]
-    lower = (100 - interval) / 200.0
-    lw = _jround(nsamp * lower)
-    hi = _jround(nsamp * (1.0 - lower))
+    lw, hi = _summary_ranks(nsamp, interval)
     if lw < 1 or hi > nsamp:
         raise IndexError("BoundsError: nsamp=%d too small for a %d%% interval" % (nsamp, interval))
-    gs = np.sort(g, axis=0)
-    q = g.shape[1]
-    V = int((-1 + math.sqrt(1 + 8 * q)) / 2)
+    dev = (getattr(results, "extra", None) or {}).get("device_summary")
+    if dev is not None and dev["interval"] == interval:
+        # statistics were reduced on the GPU at the end of Fit (bnr_summary): only rounding and the tables remain
+        mean, lo, up, xm, V = dev["mean"], dev["lower"], dev["upper"], dev["xi_mean"], dev["V"]
+    else:
+        # a different interval than the one reduced on the device: order statistics of chain 1's returned table
+        if "gamma" not in results.state:
+            raise ValueError("Summary(interval=%s) needs the gamma/xi table: call Fit with return_state='gamma_xi' "
+                             "or 'full' (the device-side summary was computed for interval=%s only)"
+                             % (interval, dev["interval"] if dev else None))
+        g = np.asarray(results.state["gamma"])[nburn:total, :, 0]
+        x = np.asarray(results.state["xi"])[nburn:total, :, 0]
+        gs = np.sort(g, axis=0)
+        mean, lo, up, xm = g.mean(axis=0), gs[lw - 1], gs[hi - 1], x.mean(axis=0)
+        V = int((-1 + math.sqrt(1 + 8 * g.shape[1])) / 2)
     node1 = np.concatenate([np.full(V - k, k + 1, dtype=np.int64) for k in range(V)])
     node2 = np.concatenate([np.arange(k + 1, V + 1, dtype=np.int64) for k in range(V)])
-    edge = dict(node1=node1, node2=node2, estimate=np.round(g.mean(axis=0), digits),
-                lower_bound=np.round(gs[lw - 1], digits), upper_bound=np.round(gs[hi - 1], digits))
-    nodes = dict(probability=np.round(x.mean(axis=0), digits))
+    edge = dict(node1=node1, node2=node2, estimate=np.round(mean, digits),
+                lower_bound=np.round(lo, digits), upper_bound=np.round(up, digits))
+    nodes = dict(probability=np.round(xm, digits))
     return BNRSummary(edge, nodes, interval)

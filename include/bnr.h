@@ -182,6 +182,28 @@ int bnr_status(bnr_handle* h, int32_t* status_per_chain);
 
 /* copy the moments buffer into caller-owned DEVICE memory (e.g. the input of an NCCL all-gather) */
 int bnr_export_moments(bnr_handle* h, double* dev_dst);
+/* Summary on the device (Summary, src/gibbs.jl:1214-1250) over trace rows [first_row, first_row + nrows) of one
+ * chain: per-edge mean and the order statistics sort(gamma_j)[rank_lo], sort(gamma_j)[rank_hi] (1-based ranks =
+ * the reference's lw / hi indices, exact: radix select, no interpolation), per-node mean xi.  Outputs are HOST
+ * arrays of q, q, q and V doubles (any may be NULL); rounding to 3 digits stays in the host wrapper. */
+int bnr_summary(bnr_handle* h, int32_t chain, int64_t first_row, int64_t nrows, int64_t rank_lo, int64_t rank_hi,
+                double* gamma_mean, double* gamma_lo, double* gamma_hi, double* xi_mean);
+
+/* Effective sample size of xi (V) and gamma (q) over trace rows [first_row, first_row + nrows) of ALL chains
+ * (BASELINE metric "gamma ESS/sec"; the reference has no ESS - estimator: multi-chain Geyer initial monotone
+ * sequence on per-chain-centred autocovariances, no rank normalisation, lags 0..max_lag computed directly).
+ * bnr_ess = accumulate + finish for this handle's chains.  Multi-GPU: every rank calls bnr_ess_accumulate, the
+ * host all-gathers the two device buffers of bnr_ess_device (autocovariance sums [max_lag+1][V+q] and chain means
+ * [chains][V+q]) and calls bnr_ess_from_stats on the gathered DEVICE buffers (nparts = ranks). Needs
+ * trace_gamma_xi_all.  max_lag is clamped to an odd value <= nrows-1; bnr_ess_device reports the value used. */
+int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma);
+int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag);
+int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov, double** chain_mean, int64_t* n_mean,
+                   int32_t* max_lag);
+int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts, const double* dev_chain_means,
+                       int32_t total_chains, int32_t V, int32_t q, int64_t nrows, int32_t max_lag, double* ess_xi,
+                       double* ess_gamma);
+
 /* which gamma formulation the handle runs (BNR_GAMMA_NFORM / BNR_GAMMA_QFORM; AUTO is resolved at create) */
 int bnr_gamma_mode(bnr_handle* h, int32_t* mode);
 /* number of CUDA kernels launched by bnr_run on this handle so far (graph replays counted per kernel node) */

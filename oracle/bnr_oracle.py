@@ -504,6 +504,39 @@ def rhat_from_moments(mean, m2, h):
     return out
 
 
+def ess_geyer(x, max_lag=None):
+    """Multi-chain effective sample size of one scalar parameter; x: (draws, chains).
+    NOT in the reference (BayesianNetworkRegression.jl computes no ESS; BASELINE.json asks for "gamma ESS/sec").
+    Estimator (Geyer 1992 initial monotone sequence, multi-chain form of Vehtari et al. 2021 / Stan, without
+    rank-normalisation, as MCMCDiagnosticTools' ess with the default estimator):
+      acov_c(t) biased per-chain autocovariance, W = mean_c acov_c(0) n/(n-1), var+ = W (n-1)/n + var(chain means),
+      rho_t = 1 - (W - mean_c acov_c(t)) / var+,  P_k = rho_2k + rho_2k+1 truncated at the first negative pair and
+      made non-increasing,  tau = -1 + 2 sum P_k,  ESS = n m / max(tau, 1/log10(n m)).
+    max_lag (odd) bounds the lags that may be used, mirroring the device kernel's lag budget."""
+    x = np.asarray(x, dtype=np.float64)
+    n, m = x.shape
+    xc = x - x.mean(axis=0, keepdims=True)
+    L = n - 1 if max_lag is None else min(int(max_lag), n - 1)
+    acov = np.stack([(xc[: n - t] * xc[t:]).sum(axis=0) / n for t in range(L + 1)])      # (L+1, m), direct lags
+    W = acov[0].mean() * n / (n - 1)
+    B_over_n = x.mean(axis=0).var(ddof=1) if m > 1 else 0.0
+    var_plus = W * (n - 1) / n + B_over_n
+    if not var_plus > 0:
+        return float("nan")
+    rho = 1.0 - (W - acov.mean(axis=1)) / var_plus
+    tau, prev, t = -1.0, np.inf, 0
+    while t + 1 <= L and t + 1 < n:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        pair = min(pair, prev)
+        tau += 2.0 * pair
+        prev = pair
+        t += 2
+    nm = n * m
+    return float(nm / max(tau, 1.0 / math.log10(max(nm, 10))))
+
+
 def julia_round(x):
     """Julia round(): ties to even."""
     return int(np.rint(x))

@@ -123,6 +123,20 @@ def test_fit_summary_dropin(bnr, tmp_path):
         np.testing.assert_array_equal(out.edge_coef[k], want[k], err_msg=k)
     np.testing.assert_array_equal(out.prob_nodes["probability"], want["probability"])
     assert out.ci_level == 95
+    assert res.extra["device_summary"] is not None and res.extra["gamma_mode"] in ("nform", "qform")
+    # the same fit without copying any table back: Summary comes from the device reduction alone
+    res0 = bnr.Fit(Xl, y, 5, nburn=300, nsamples=100, psrf_cutoff=1e9, num_chains=2, seed=1234, filename=None,
+                   return_state="none")
+    out0 = bnr.Summary(res0)
+    assert len(res0.state) == 0
+    for k in ("estimate", "lower_bound", "upper_bound"):
+        np.testing.assert_array_equal(out0.edge_coef[k], out.edge_coef[k], err_msg=k)
+    np.testing.assert_array_equal(out0.prob_nodes["probability"], out.prob_nodes["probability"])
+    out90 = bnr.Summary(res, interval=90)        # not the interval reduced on the device: host order statistics
+    want90 = O.summary(st["γ"][300:400, :, 0], st["ξ"][300:400, :, 0], interval=90)
+    np.testing.assert_array_equal(out90.edge_coef["upper_bound"], want90["upper_bound"])
+    with pytest.raises(ValueError):
+        bnr.Summary(res0, interval=90)
     with pytest.raises(IndexError):
         bnr.Summary(bnr.Results(bnr.Table(gamma=st["γ"][:10], xi=st["ξ"][:10]), [], [], 0, 10))
 
@@ -317,3 +331,52 @@ def test_qform_full_size_properties(bnr):
         st = eng.get_state_dict(2)
         assert eng.iteration == 8 and not (eng.status() & ~1).any()
         assert np.isfinite(st["gamma"]).all() and (st["S"] > 0).all() and st["tau2"] > 0
+
+
+def test_device_summary_and_ess_match_oracle(bnr, golden):
+    """Device Summary (radix-select order statistics) == the oracle's sort-based Summary bit for bit on the bounds;
+    device ESS == the oracle's Geyer estimator on the same traces."""
+    X, y = golden["test1.X"], golden["test1.y"]
+    nburn, nsamp, C = 150, 333, 5
+    with bnr.Engine(X, y, 5, num_chains=C, seed=11, trace_rows=nburn + nsamp + 1, trace_full_chains=2) as eng:
+        eng.init_state()
+        eng.run(nburn + nsamp)
+        lw, hi = O.julia_round(nsamp * 0.025), O.julia_round(nsamp * 0.975)
+        for chain in (0, 3):                       # chain 0 is read from the full-state trace, chain 3 from the gamma/xi trace
+            g = eng.get_trace(chain, "gamma", nburn + 1, nburn + nsamp + 1)[:, :, 0]
+            x = eng.get_trace(chain, "xi", nburn + 1, nburn + nsamp + 1)[:, :, 0]
+            gm, gl, gh, xm = eng.summary(chain, nburn + 1, nsamp, lw, hi)
+            gs = np.sort(g, axis=0)
+            np.testing.assert_array_equal(gl, gs[lw - 1])
+            np.testing.assert_array_equal(gh, gs[hi - 1])
+            np.testing.assert_allclose(gm, g.mean(axis=0), rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(xm, x.mean(axis=0), rtol=1e-12, atol=1e-14)
+            want = O.summary(g, x)
+            np.testing.assert_allclose(np.round(gm, 3), want["estimate"], atol=1.001e-3)
+            np.testing.assert_array_equal(np.round(gl, 3), want["lower_bound"])
+            np.testing.assert_array_equal(np.round(gh, 3), want["upper_bound"])
+        # extreme ranks = min / max
+        gm, gl, gh, xm = eng.summary(0, nburn + 1, nsamp, 1, nsamp)
+        g = eng.get_trace(0, "gamma", nburn + 1, nburn + nsamp + 1)[:, :, 0]
+        np.testing.assert_array_equal(gl, g.min(axis=0))
+        np.testing.assert_array_equal(gh, g.max(axis=0))
+        with pytest.raises(bnr.BnrError):
+            eng.summary(0, nburn + 1, nsamp, 0, nsamp)
+        # ESS
+        L = 63
+        ex, eg = eng.ess(nburn + 1, nsamp, L)
+        G = np.stack([eng.get_trace(c, "gamma", nburn + 1, nburn + nsamp + 1)[:, :, 0] for c in range(C)], axis=2)
+        Xi = np.stack([eng.get_trace(c, "xi", nburn + 1, nburn + nsamp + 1)[:, :, 0] for c in range(C)], axis=2)
+        for j in list(range(0, G.shape[1], 7)):
+            np.testing.assert_allclose(eg[j], O.ess_geyer(G[:, j, :], L), rtol=1e-8, err_msg="gamma %d" % j)
+        for k in range(Xi.shape[1]):
+            want = O.ess_geyer(Xi[:, k, :], L)
+            if math.isnan(want):
+                assert math.isnan(ex[k])
+            else:
+                np.testing.assert_allclose(ex[k], want, rtol=1e-8, err_msg="xi %d" % k)
+        # gathered form: two "ranks" holding the same statistics = one handle with every chain counted twice
+        (pa, na), (pm, nm), lag = eng.ess_device()
+        assert lag == L and na == (L + 1) * (eng.V + eng.q) and nm == C * (eng.V + eng.q)
+        ex1, eg1 = eng.ess_from_stats(pa, 1, pm, C, nsamp, lag)
+        np.testing.assert_array_equal(eg1, eg)

@@ -276,3 +276,29 @@ def test_qform_gamma_draw_has_the_reference_conditional_law():
     np.testing.assert_allclose(c["gamma"], b["gamma"] + np.linalg.solve(b["L"].T, z), rtol=1e-10, atol=1e-12)
     m, P = O.gamma_conditional_moments(X, y, tau2, b["W"], S, mu)
     np.testing.assert_allclose(m, b["mean"], rtol=1e-9, atol=1e-11)
+
+
+def test_ess_estimator_known_answers():
+    """oracle.ess_geyer: iid draws give ESS ~ n m; an AR(1) chain with coefficient phi gives n m (1-phi)/(1+phi);
+    the direct-lag form equals the FFT form used elsewhere."""
+    rng = np.random.default_rng(0)
+    n, m = 4000, 4
+    iid = rng.normal(size=(n, m))
+    e = O.ess_geyer(iid)
+    assert 0.85 * n * m < e < 1.2 * n * m
+    phi = 0.7
+    x = np.zeros((n, m))
+    eps = rng.normal(size=(n, m))
+    for t in range(1, n):
+        x[t] = phi * x[t - 1] + eps[t]
+    e = O.ess_geyer(x, max_lag=255)
+    want = n * m * (1 - phi) / (1 + phi)
+    assert 0.8 * want < e < 1.25 * want
+    # FFT cross-check of the autocovariances behind it
+    xc = x - x.mean(axis=0)
+    f = np.fft.rfft(xc, n=2 * n, axis=0)
+    ac_fft = np.fft.irfft(f * np.conj(f), axis=0)[:8] / n
+    ac_dir = np.stack([(xc[: n - t] * xc[t:]).sum(axis=0) / n for t in range(8)])
+    np.testing.assert_allclose(ac_fft, ac_dir, rtol=1e-9, atol=1e-12)
+    # a stuck chain (zero variance) is NaN, never a crash
+    assert math.isnan(O.ess_geyer(np.ones((100, 2))))
