@@ -32,12 +32,31 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
                   std::string(#call) + ": " + cudaGetErrorString(_e));                                   \
   } while (0)
 
+// A chain group: a contiguous slice of the handle's chains advanced by its own stream and its own two-sweep CUDA
+// graph.  Groups never synchronise with each other inside bnr_run, so while one group sits in its latency-bound
+// phases (Cholesky panels, triangular solves, per-chain scalar kernels: <= one CTA per chain) the other group's
+// DMMA SYRK keeps the remaining SMs busy.  Results do not depend on the grouping (RNG keyed by global chain id).
+struct ChainGroup {
+  Engine e;                      // view of the handle's arrays restricted to chains [c0, c0 + e.d.C)
+  int c0 = 0;
+  cudaStream_t stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  cudaEvent_t done = nullptr;
+  double* ws = nullptr;          // split-K workspace of this group
+  long long* counters = nullptr; // device [2]: iter, trace_row of this group
+  long long* mom_window = nullptr;
+};
+constexpr int MAX_GROUPS = 4;
+
 struct bnr_handle {
   bnr_params p;
   Engine e;
   cudaStream_t stream = nullptr;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
+  ChainGroup groups[MAX_GROUPS];
+  int n_groups = 0;
+  bool graphs_ready = false;
+  cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<void*> allocs;
   double* ws = nullptr;          // split-K workspace
@@ -45,9 +64,9 @@ struct bnr_handle {
   long long inj_len = 0;
   bool aux_on = false;
   Aux aux_saved = {};
-  long long mom_half = 0;
+ long long mom_half = 0;        // draws per split chain behind the current moments buffer
   long long launches = 0;        // kernels launched by bnr_run so far (graph replays included)
-  long long graph_kernels = 0;   // kernels inside the captured two-sweep graph        // draws per split chain behind the current moments buffer
+  long long graph_kernels = 0;   // kernels inside the captured two-sweep graphs (all groups)
   bool xg_valid = false;         // e.xg == X * gamma for the current state
   bool ran = false;
   double* d_rhat = nullptr;      // [V+q]
@@ -226,6 +245,29 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
     int r = dalloc(h, &e.tr_gx, C * e.trace_rows * (d.V + d.q), false);
     if (r) return r;
   }
+  {
+    // chain groups (see ChainGroup): 2 by default once there are enough chains to split
+    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 4 ? 2 : 1);
+    if (ng > MAX_GROUPS) ng = MAX_GROUPS;
+    if (ng > d.C) ng = d.C;
+    h->n_groups = ng;
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int g = 0; g < ng; ++g) {
+      ChainGroup& G = h->groups[g];
+      // descending priorities break the symmetry between the groups: group 0's grids are dispatched first, so the
+      // groups drift half a sweep apart and one group's SYRK fills the SMs the other leaves idle in its panel phases
+      int plo = 0, phi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));       // plo = least, phi = greatest (numerically lower)
+      int prio = phi + g;
+      if (prio > plo) prio = plo;
+      if (getenv("BNR_NO_PRIO")) prio = plo;
+      CK(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio));
+      CK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+      DA(G.ws, x_times_workspace_doubles(d));
+      DA(G.counters, 2);
+      DA(G.mom_window, 2);
+    }
+  }
   h->tmp_doubles = (size_t)1 << 22;
   DA(h->d_tmp, h->tmp_doubles);
   e.inj = nullptr; e.inj_stride = 0;
@@ -235,12 +277,18 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   return BNR_OK;
 }
 
+static void drop_graph(bnr_handle* h);
+
 extern "C" int bnr_destroy(bnr_handle* h) {
   if (!h) return BNR_OK;
   cudaSetDevice(h->p.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->gexec) cudaGraphExecDestroy(h->gexec);
-  if (h->graph) cudaGraphDestroy(h->graph);
+  drop_graph(h);
+  for (int g = 0; g < h->n_groups; ++g) {
+    if (h->groups[g].stream) { cudaStreamSynchronize(h->groups[g].stream); cudaStreamDestroy(h->groups[g].stream); }
+    if (h->groups[g].done) cudaEventDestroy(h->groups[g].done);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -250,8 +298,12 @@ extern "C" int bnr_destroy(bnr_handle* h) {
 }
 
 static void drop_graph(bnr_handle* h) {
-  if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
-  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  for (int g = 0; g < h->n_groups; ++g) {
+    ChainGroup& G = h->groups[g];
+    if (G.gexec) { cudaGraphExecDestroy(G.gexec); G.gexec = nullptr; }
+    if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+  }
+  h->graphs_ready = false;
 }
 
 // X * gamma for the current state (cache used by tau2 and mu)
@@ -261,15 +313,13 @@ static void refresh_xg(bnr_handle* h) {
 }
 
 // the gamma conditional: W, v, X v, rhs, G, Cholesky, solves, X' a4, gamma (and optionally S + lambda statistics)
-static void run_gamma(bnr_handle* h, int gig_flags) {
-  Engine& e = h->e;
-  cudaStream_t s = h->stream;
+static void run_gamma(Engine& e, double* ws, cudaStream_t s, int gig_flags) {
   if (e.d.gmode == BNR_GAMMA_QFORM) {
     // P = (X'X + D^-1)/tau2 = L L';  L w = X'(y - mu - X W)/tau2;  L' beta = w + z;  gamma = W + beta
     launch_edge_prep(e, 2, s);                        // W, v = z
-    launch_x_times(e, 0, e.W, e.xv, h->ws, s);        // X W
+    launch_x_times(e, 0, e.W, e.xv, ws, s);           // X W
     launch_rhs(e, s);                                 // (y - mu - X W)/tau2
-    launch_x_times(e, 1, e.rhs, e.t, h->ws, s);       // t = X' rhs
+    launch_x_times(e, 1, e.rhs, e.t, ws, s);          // t = X' rhs
     launch_build_P(e, s);
     launch_cholesky(e, e.t, s);
     launch_chol_solve(e, e.t, e.v, s);
@@ -277,40 +327,76 @@ static void run_gamma(bnr_handle* h, int gig_flags) {
     return;
   }
   launch_edge_prep(e, 1, s);
-  launch_x_times(e, 0, e.v, e.xv, h->ws, s);
+  launch_x_times(e, 0, e.v, e.xv, ws, s);
   launch_rhs(e, s);
   launch_syrk_G(e, s);
   launch_cholesky(e, e.rhs, s);
   launch_chol_solve(e, e.rhs, nullptr, s);
-  launch_x_times(e, 1, e.rhs, e.t, h->ws, s);
+  launch_x_times(e, 1, e.rhs, e.t, ws, s);
   launch_gamma_gig(e, gig_flags, s);
 }
 
 // one full sweep in gibbs_sample! order (src/gibbs.jl:663-677)
-static void enqueue_sweep(bnr_handle* h) {
-  Engine& e = h->e;
-  cudaStream_t s = h->stream;
+static void enqueue_sweep(Engine& e, double* ws, cudaStream_t s) {
   launch_tau2(e, s);
   launch_uxi(e, s);
   std::swap(e.u, e.u_alt);          // u now holds the new draw (pointer swap is baked per captured sweep)
-  run_gamma(h, 3);
-  launch_x_times(e, 0, e.gamma, e.xg, h->ws, s);
+  run_gamma(e, ws, s, 3);
+  launch_x_times(e, 0, e.gamma, e.xg, ws, s);
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
                        (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
   launch_record(e, 1, s);
   launch_advance(e, 1, s);
 }
 
-// The u double buffer flips every sweep, so the graph holds TWO sweeps; odd counts run one sweep eagerly.
-static int build_graph(bnr_handle* h) {
-  if (h->gexec) return BNR_OK;
+// view of the handle's engine restricted to chains [c0, c0 + Cg): every per-chain array is chain-major, so the
+// view is the same struct with offset pointers, a smaller C and a shifted global chain id
+static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counters, long long* mom_window) {
+  Engine v = h->e;
+  const Dims& d = h->e.d;
+  const size_t c = (size_t)c0;
+  v.d.C = Cg;
+  v.d.chain_offset = d.chain_offset + c0;
+  v.tau2 += c; v.theta += c; v.Delta += c; v.mu += c; v.status += c;
+  v.u += c * d.V * d.R; v.u_alt += c * d.V * d.R; v.xi += c * d.V;
+  v.gamma += c * d.qp; v.S += c * d.qp; v.W += c * d.qp; v.v += c * d.qp; v.t += c * d.qp;
+  v.M += c * d.R * d.R; v.lambda += c * d.R; v.pi += c * 3 * d.R;
+  v.xg += c * d.np; v.xv += c * d.np; v.rhs += c * d.np;
+  v.G += c * d.gdim * d.gdim; v.dinv += c * d.gdim;
+  v.partials += c * d.nparts * (2 * MAX_R + 1);
+  v.moments += c * 2 * (d.V + d.q) * 2;
+  if (v.tr_gx) v.tr_gx += c * v.trace_rows * (d.V + d.q);
+  int tfc = h->e.trace_full_chains - c0;
+  tfc = tfc < 0 ? 0 : (tfc > Cg ? Cg : tfc);
+  v.trace_full_chains = tfc;
+  if (v.tr_full) v.tr_full += c * v.trace_rows * v.rowlen_full;
+  if (tfc == 0) v.tr_full = nullptr;
+  v.iter = counters; v.trace_row = counters + 1; v.mom_window = mom_window;
+  v.inj = nullptr; v.inj_stride = 0;
+  memset(&v.aux, 0, sizeof(v.aux));
+  return v;
+}
+
+// The u double buffer flips every sweep, so every group's graph holds TWO sweeps; odd counts run one sweep eagerly
+// on the whole chain set.
+static int build_graphs(bnr_handle* h) {
+  if (h->graphs_ready) return BNR_OK;
   const long long before = g_launches;
-  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  enqueue_sweep(h);
-  enqueue_sweep(h);
-  CK(cudaStreamEndCapture(h->stream, &h->graph));
+  const int C = h->e.d.C, ng = h->n_groups;
+  for (int g = 0; g < ng; ++g) {
+    ChainGroup& G = h->groups[g];
+    const int c0 = (int)((long long)C * g / ng), c1 = (int)((long long)C * (g + 1) / ng);
+    G.c0 = c0;
+    G.e = group_view(h, c0, c1 - c0, G.counters, G.mom_window);
+    Engine e = G.e;                  // the capture swaps u / u_alt twice on this copy
+    CK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_sweep(e, G.ws, G.stream);
+    enqueue_sweep(e, G.ws, G.stream);
+    CK(cudaStreamEndCapture(G.stream, &G.graph));
+    CK(cudaGraphInstantiate(&G.gexec, G.graph, 0));
+  }
   h->graph_kernels = g_launches - before;
-  CK(cudaGraphInstantiate(&h->gexec, h->graph, 0));
+  h->graphs_ready = true;
   return BNR_OK;
 }
 
@@ -337,17 +423,32 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
   if (!h->xg_valid) { const long long b0 = g_launches; refresh_xg(h); h->launches += g_launches - b0; }
   int64_t left = n_iters;
   if (h->e.inj == nullptr && !h->aux_on && left >= 2) {
-    int r = build_graph(h);
+    int r = build_graphs(h);
     if (r) return r;
+    // fork: every group starts from the handle's counters and runs its sweeps without ever meeting the others
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    for (int g = 0; g < h->n_groups; ++g) {
+      ChainGroup& G = h->groups[g];
+      CK(cudaStreamWaitEvent(G.stream, h->ev_fork, 0));
+      CK(cudaMemcpyAsync(G.counters, h->e.iter, sizeof(long long), cudaMemcpyDeviceToDevice, G.stream));
+      CK(cudaMemcpyAsync(G.counters + 1, h->e.trace_row, sizeof(long long), cudaMemcpyDeviceToDevice, G.stream));
+    }
     for (; left >= 2; left -= 2) {
-      CK(cudaGraphLaunch(h->gexec, h->stream));
+      for (int g = 0; g < h->n_groups; ++g) CK(cudaGraphLaunch(h->groups[g].gexec, h->groups[g].stream));
       h->launches += h->graph_kernels;
     }
+    // join
+    for (int g = 0; g < h->n_groups; ++g) {
+      CK(cudaEventRecord(h->groups[g].done, h->groups[g].stream));
+      CK(cudaStreamWaitEvent(h->stream, h->groups[g].done, 0));
+    }
+    CK(cudaMemcpyAsync(h->e.iter, h->groups[0].counters, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->e.trace_row, h->groups[0].counters + 1, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
   }
   for (; left > 0; --left) {
-    drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graph
+    drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graphs
     const long long before = g_launches;
-    enqueue_sweep(h);
+    enqueue_sweep(h->e, h->ws, h->stream);
     h->launches += g_launches - before;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -431,6 +532,8 @@ extern "C" int bnr_set_moment_window(bnr_handle* h, int64_t first, int64_t len) 
   if (!h || len < 0) return fail(BNR_EINVAL, "bad arguments");
   long long w[2] = {first, len};
   CK(cudaMemcpyAsync(h->e.mom_window, w, sizeof(w), cudaMemcpyHostToDevice, h->stream));
+  for (int g = 0; g < h->n_groups; ++g)
+    CK(cudaMemcpyAsync(h->groups[g].mom_window, w, sizeof(w), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->mom_half = len / 2;
   return BNR_OK;
@@ -754,7 +857,7 @@ extern "C" int bnr_step(bnr_handle* h, int32_t cond) {
       std::swap(e.u, e.u_alt);
       break;
     case BNR_COND_GAMMA:
-      run_gamma(h, 1);
+      run_gamma(h->e, h->ws, h->stream, 1);
       h->xg_valid = false;
       break;
     case BNR_COND_D:

@@ -63,12 +63,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // 1 KB rows.  A dedicated producer warp streams them into a 4-stage shared-memory ring with TMA-engine bulk
 // copies (cp.async.bulk, completion on "full" mbarriers); the 8 consumer warps never execute a block-wide
 // barrier in the main loop - they wait on "full", issue DMMA m8n8k4, and release the stage on "empty".
-// CTA tile 128 x 128, k-step 16, consumer warps 2 (along j) x 4 (along i), warp tile 64(j) x 32(i): the MMA
-// "M" dimension runs along j (columns of C) and "N" along i (rows of C), so every accumulator pair is two
-// consecutive rows of one column of the column-major C -> 16-byte stores.  Shared rows are padded to 132
-// doubles (== 4 mod 16) which makes the (row, k) fragment loads bank-conflict free.
-// Work that cannot contribute is skipped: diagonal tiles compute only their lower triangle (balanced over the
-// warps, see syrk_diag_tile), and warp tiles that lie entirely in the zero padding beyond n are not issued.
+// CTA tile 128 x 128, k-step 16.  The MMA "M" dimension runs along j (columns of C) and "N" along i (rows of C), so
+// every accumulator pair is two consecutive rows of one column of the column-major C -> 16-byte stores.  Strictly
+// lower tiles use a column-strip warp layout (syrk_strip_tile: 2 column fragments x all row fragments per warp),
+// diagonal tiles compute only their lower triangle, balanced over the warps (syrk_diag_tile).  Shared rows are
+// padded to 132 doubles (== 4 mod 16) which makes the (row, k) fragment loads bank-conflict free.
+// The per-chain scale s_c[k] is applied to the operand with the fewest fragments per warp (2): DMUL shares the
+// FP64 pipe with DMMA.  Work that cannot contribute is skipped: the symmetric half of diagonal tiles and row
+// fragments that lie entirely in the zero padding beyond n.
 // grid = (C, tiles), block = 384 (2 consumer warpgroups + 1 producer warpgroup, registers re-balanced with
 // setmaxnreg: 232 per consumer thread, 40 per producer thread); dynamic smem = SYRK_SMEM.
 // ------------------------------------------------------------------------------------------------------------
@@ -81,74 +83,6 @@ constexpr int SY_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgrou
 constexpr int SY_PRODUCER_REGS = 40, SY_CONSUMER_REGS = 232;   // 128*40 + 256*232 = 64512 = 384*168
 constexpr size_t SYRK_SMEM = (size_t)SY_STAGES * SY_STAGE_DBL * sizeof(double) + 2 * SY_STAGES * sizeof(unsigned long long);
 
-// fragments of one k4-step: 8 A fragments (rows of the j operand) and 4 scaled B fragments (rows of the i operand)
-template <int MODE>
-__device__ __forceinline__ void syrk_load_frags(const double* __restrict__ sj, const double* __restrict__ si,
-                                                const double* __restrict__ ss, int k4, int wj, int wi, int lk, int lr,
-                                                double (&af)[8], double (&bf)[4]) {
-  const int kr = k4 * 4 + lk;
-#ifdef SYRK_LAB_NOLDS
-#pragma unroll
-  for (int mf = 0; mf < 8; ++mf) af[mf] = 1.0 + mf + kr;
-#pragma unroll
-  for (int nf = 0; nf < 4; ++nf) bf[nf] = 2.0 + nf + kr;
-#else
-#pragma unroll
-  for (int mf = 0; mf < 8; ++mf) af[mf] = sj[kr * SY_LDS + wj * 64 + mf * 8 + lr];
-#ifdef SYRK_LAB_NOSCALE
-#pragma unroll
-  for (int nf = 0; nf < 4; ++nf) bf[nf] = si[kr * SY_LDS + wi * 32 + nf * 8 + lr];
-#else
-  const double sk = (MODE == 0) ? ss[kr] : 1.0;
-#pragma unroll
-  for (int nf = 0; nf < 4; ++nf) bf[nf] = si[kr * SY_LDS + wi * 32 + nf * 8 + lr] * sk;
-#endif
-#endif
-}
-
-__device__ __forceinline__ void syrk_mma(double (&acc)[8][4][2], const double (&af)[8], const double (&bf)[4]) {
-#pragma unroll
-  for (int mf = 0; mf < 8; ++mf)
-#pragma unroll
-    for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
-}
-
-// consumer main loop: fragments of k4-step t+1 are fetched from shared memory (and scaled) while the 32 DMMAs of
-// step t are in flight, across stage boundaries too, so no LDS / DMUL latency is exposed to the FP64 pipe.
-template <int MODE>
-__device__ __forceinline__ void syrk_mainloop(const double* __restrict__ smem, unsigned long long* full,
-                                              unsigned long long* empty, int nk, double (&acc)[8][4][2],
-                                              int wj, int wi, int lk, int lr, int lane) {
-  double af[2][8], bf[2][4];
-  auto stage_ptrs = [&](int kt, const double*& sj, const double*& si, const double*& ss) {
-    sj = smem + (size_t)(kt % SY_STAGES) * SY_STAGE_DBL;
-    si = sj + SY_BK * SY_LDS;
-    ss = sj + 2 * SY_BK * SY_LDS;
-  };
-  const double *sj, *si, *ss;
-  mbar_wait(&full[0], 0);
-  stage_ptrs(0, sj, si, ss);
-  syrk_load_frags<MODE>(sj, si, ss, 0, wj, wi, lk, lr, af[0], bf[0]);
-  for (int kt = 0; kt < nk; ++kt) {
-#pragma unroll
-    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
-      const int cur = k4 & 1, nxt = cur ^ 1;
-      if (k4 + 1 < SY_BK / 4) {
-        syrk_load_frags<MODE>(sj, si, ss, k4 + 1, wj, wi, lk, lr, af[nxt], bf[nxt]);
-      } else if (kt + 1 < nk) {
-        const double *nj, *ni, *ns;
-        mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
-        stage_ptrs(kt + 1, nj, ni, ns);
-        syrk_load_frags<MODE>(nj, ni, ns, 0, wj, wi, lk, lr, af[nxt], bf[nxt]);
-      }
-      syrk_mma(acc, af[cur], bf[cur]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
-    stage_ptrs(kt + 1, sj, si, ss);
-  }
-}
-
 // Diagonal tiles: only the lower triangle of the 128 x 128 tile is needed.  Seen as 16 x 16 fragments of 8 x 8,
 // fragment column j holds 16 - j useful fragments; warp W takes columns W and 15 - W (17 fragments, the same for
 // every warp), so the symmetric half is skipped AND the four SM sub-partitions stay evenly loaded.  W is a template
@@ -159,11 +93,18 @@ __device__ __forceinline__ void syrk_diag_frags(const double* __restrict__ sj, c
                                                 int lk, int lr, double (&a2)[2], double (&bfr)[16 - W]) {
   const int kr = k4 * 4 + lk;
   const double* row = sj + kr * SY_LDS + lr;
-  const double sk = (MODE == 0) ? ss[kr] : 1.0;
-  a2[0] = row[W * 8];
-  a2[1] = row[(15 - W) * 8];
+  // the scale rides on the two column-operand fragments (2 DMULs) rather than on the 16 - W row-operand fragments:
+  // DMUL shares the FP64 pipe with DMMA, so every multiply saved is tensor throughput gained
+  if (MODE == 0) {
+    const double sk = ss[kr];
+    a2[0] = row[W * 8] * sk;
+    a2[1] = row[(15 - W) * 8] * sk;
+  } else {
+    a2[0] = row[W * 8];
+    a2[1] = row[(15 - W) * 8];
+  }
 #pragma unroll
-  for (int i = 0; i < 16 - W; ++i) bfr[i] = row[(W + i) * 8] * sk;
+  for (int i = 0; i < 16 - W; ++i) bfr[i] = row[(W + i) * 8];
 }
 
 template <int MODE, int W>
@@ -215,6 +156,85 @@ __device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, 
       v.y -= acc[t][1];
     }
     *p = v;
+  }
+}
+
+// Off-diagonal tiles, "column-strip" warp layout: warp w owns the two 8-column fragments 2w, 2w+1 of the tile
+// (columns j0 + 16w .. j0 + 16w + 15 of C) and ALL NF 8-row fragments of the i operand, i.e. 2 x NF DMMAs per k4-step.
+// Compared with a 64 x 32 warp tile this (a) halves the DMULs: the per-chain scale rides on the 2 column-operand
+// fragments, (b) lets a tile of the last block row stop at the last fragment that holds a valid row (NF < 16):
+// the zero padding of n up to a multiple of 128 costs no tensor work.
+template <int MODE, int NF>
+__device__ __forceinline__ void syrk_strip_frags(const double* __restrict__ sj, const double* __restrict__ si,
+                                                 const double* __restrict__ ss, int k4, int warp, int lk, int lr,
+                                                 double (&af)[2], double (&bf)[NF]) {
+  const int kr = k4 * 4 + lk;
+  const double* rj = sj + kr * SY_LDS + warp * 16 + lr;
+  const double* ri = si + kr * SY_LDS + lr;
+  if (MODE == 0) {
+    const double sk = ss[kr];
+    af[0] = rj[0] * sk;
+    af[1] = rj[8] * sk;
+  } else {
+    af[0] = rj[0];
+    af[1] = rj[8];
+  }
+#pragma unroll
+  for (int nf = 0; nf < NF; ++nf) bf[nf] = ri[nf * 8];
+}
+
+template <int MODE, int NF>
+__device__ __forceinline__ void syrk_strip_tile(const double* __restrict__ smem, unsigned long long* full,
+                                                unsigned long long* empty, int nk, int warp, int lk, int lr, int lane,
+                                                double* __restrict__ Cc, int np, int i0, int j0) {
+  double acc[2][NF][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < NF; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  double af[2][2], bf[2][NF];
+  mbar_wait(&full[0], 0);
+  const double* sj = smem;
+  syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, 0, warp, lk, lr, af[0], bf[0]);
+  for (int kt = 0; kt < nk; ++kt) {
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      const int cur = k4 & 1, nxt = cur ^ 1;
+      if (k4 + 1 < SY_BK / 4) {
+        syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, k4 + 1, warp, lk, lr, af[nxt], bf[nxt]);
+      } else if (kt + 1 < nk) {
+        mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
+        const double* nj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
+        syrk_strip_frags<MODE, NF>(nj, nj + SY_BK * SY_LDS, nj + 2 * SY_BK * SY_LDS, 0, warp, lk, lr, af[nxt], bf[nxt]);
+      }
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) {
+        dmma884(acc[0][nf][0], acc[0][nf][1], af[cur][0], bf[cur][nf]);
+        dmma884(acc[1][nf][0], acc[1][nf][1], af[cur][1], bf[cur][nf]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
+    sj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
+  }
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf) {
+    const int j = j0 + warp * 16 + mf * 8 + lr;
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) {
+      const int i = i0 + nf * 8 + 2 * lk;
+      double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
+      double2 v;
+      if (MODE == 0) {
+        v.x = acc[mf][nf][0];
+        v.y = acc[mf][nf][1];
+      } else {
+        v = *p;
+        v.x -= acc[mf][nf][0];
+        v.y -= acc[mf][nf][1];
+      }
+      *p = v;
+    }
   }
 }
 
@@ -306,49 +326,18 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     return;
   }
 
-  double acc[8][4][2];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-
-  const int wj = warp >> 2, wi = warp & 3;
-  // fragments (8 rows) that hold at least one valid row; rows >= nvalid are zero padding
-  int mf_cnt = (nvalid - (j0 + wj * 64) + 7) / 8;
-  int nf_cnt = (nvalid - (i0 + wi * 32) + 7) / 8;
-  mf_cnt = mf_cnt < 0 ? 0 : (mf_cnt > 8 ? 8 : mf_cnt);
-  nf_cnt = nf_cnt < 0 ? 0 : (nf_cnt > 4 ? 4 : nf_cnt);
-  const bool all_pad = (mf_cnt == 0 || nf_cnt == 0);      // X rows there are zero: the product is exactly 0
-
-  if (all_pad) {
-    // still take part in the stage hand-shake so the producer can recycle the ring
-    for (int kt = 0; kt < nk; ++kt) {
-      mbar_wait(&full[kt % SY_STAGES], (kt / SY_STAGES) & 1);
-      if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
-    }
-  } else {
-    syrk_mainloop<MODE>(smem, full, empty, nk, acc, wj, wi, lk, lr, lane);
-  }
-  if (all_pad && MODE == 1) return;        // nothing to subtract; MODE 0 still stores 0 (+ identity on a diagonal)
-
-#pragma unroll
-  for (int mf = 0; mf < 8; ++mf) {
-    const int j = j0 + wj * 64 + mf * 8 + lr;
-#pragma unroll
-    for (int nf = 0; nf < 4; ++nf) {
-      const int i = i0 + wi * 32 + nf * 8 + 2 * lk;
-      double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
-      double2 v;
-      if (MODE == 0) {
-        v.x = acc[mf][nf][0];
-        v.y = acc[mf][nf][1];
-      } else {
-        v = *p;
-        v.x -= acc[mf][nf][0];
-        v.y -= acc[mf][nf][1];
-      }
-      *p = v;
-    }
+  // strictly-lower tile: only the 8-row fragments of the i operand that hold a valid row are computed and stored.
+  // Rows >= nvalid are zero padding: their entries of C are exactly zero, were zero-initialised at allocation and
+  // are never written by any kernel, so skipping them changes nothing.
+  int nfv = (nvalid - i0 + 7) / 8;
+  nfv = nfv > 16 ? 16 : nfv;
+  switch (nfv) {
+#define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
+    BNR_STRIP_CASE(1) BNR_STRIP_CASE(2) BNR_STRIP_CASE(3) BNR_STRIP_CASE(4) BNR_STRIP_CASE(5) BNR_STRIP_CASE(6)
+    BNR_STRIP_CASE(7) BNR_STRIP_CASE(8) BNR_STRIP_CASE(9) BNR_STRIP_CASE(10) BNR_STRIP_CASE(11) BNR_STRIP_CASE(12)
+    BNR_STRIP_CASE(13) BNR_STRIP_CASE(14) BNR_STRIP_CASE(15)
+#undef BNR_STRIP_CASE
+    default: syrk_strip_tile<MODE, 16>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
   }
 }
 
@@ -837,14 +826,13 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
 void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
-  const int nvalid = d.gmode == 2 ? d.q : d.n;    // rows beyond are identity padding
+  const int nvalid = d.gmode == 2 ? d.q : d.n;    // rows beyond are identity padding: exact zeros off the diagonal
   const size_t cs = (size_t)N * N;
   const int T = N / PB;
-  (void)nvalid;
   for (int J = 0; J < T; ++J) {
     if (J > 0) {
       dim3 g2(d.C, T - J);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, N, J * PB / SY_BK, J);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, nvalid, J * PB / SY_BK, J);
     }
     ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, rhs, e.dinv, e.status);
     if (J + 1 < T) {

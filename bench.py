@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the config's)")
+    ap.add_argument("--chain-groups", type=int, default=0, help="independent stream/graph groups per GPU (0 = library default)")
+    ap.add_argument("--gamma-mode", default="auto", choices=["auto", "nform", "qform"])
     ap.add_argument("--dense", action="store_true", help="dense Gaussian X instead of sparse networks")
     ap.add_argument("--ref-sweeps", type=int, default=12, help="bounded CPU sample: sweeps per chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -230,7 +232,8 @@ def main():
     # ---------------- device-resident timing: `value` ----------------
     rows = Wm + K + 1 + args.profile_sweeps + 2
     eng = bnr.Engine(X, y, R, num_chains=chains, seed=20241018, chain_offset=rank * chains, device=local_rank,
-                     trace_rows=rows, trace_full_chains=1, trace_gamma_xi_all=True)
+                     trace_rows=rows, trace_full_chains=1, trace_gamma_xi_all=True, chain_groups=args.chain_groups,
+                     gamma_mode=args.gamma_mode)
     eng.init_state()
     eng.run(Wm)
     eng.set_moment_window(Wm + 1, K)
@@ -290,7 +293,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e2 = bnr.Engine(X, y, R, num_chains=chains, seed=7, chain_offset=rank * chains, device=local_rank,
-                    trace_rows=K + 1, trace_full_chains=0, trace_gamma_xi_all=True)       # H2D of X, y
+                    trace_rows=K + 1, trace_full_chains=0, trace_gamma_xi_all=True, chain_groups=args.chain_groups,
+                    gamma_mode=args.gamma_mode)                                           # H2D of X, y
     e2.init_state()
     e2.set_moment_window(1, K)
     e2.run(K)

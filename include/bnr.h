@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define BNR_VERSION 100
+#define BNR_VERSION 101
 
 /* error codes */
 #define BNR_OK 0
@@ -116,6 +116,9 @@ typedef struct bnr_params {
   double eta, zeta, iota, a_delta, b_delta, nu;   /* Fit! hyper-parameters (src/gibbs.jl:725) */
   int32_t gig_inject_len;    /* K: injected uniforms per edge in injection mode (default 64) */
   int32_t gamma_mode;        /* BNR_GAMMA_AUTO (cost model) | BNR_GAMMA_NFORM | BNR_GAMMA_QFORM              */
+  int32_t chain_groups;      /* chain groups advanced by independent streams/graphs (0 = default 2, max 4);
+                                a throughput knob only: results are identical for every value               */
+  int32_t reserved;
 } bnr_params;
 
 /* Formulation of the gamma draw (update_gamma!, src/gibbs.jl:420-438).  Both sample the same conditional

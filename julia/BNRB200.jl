@@ -15,7 +15,7 @@ struct BnrParams
     chain_offset::Int32; device::Int32; trace_full_chains::Int32; trace_gamma_xi_all::Int32
     trace_rows::Int64; seed::UInt64
     eta::Float64; zeta::Float64; iota::Float64; a_delta::Float64; b_delta::Float64; nu::Float64
-    gig_inject_len::Int32; reserved::Int32
+    gig_inject_len::Int32; gamma_mode::Int32; chain_groups::Int32; reserved::Int32
 end
 
 function check(code::Cint)
@@ -38,7 +38,7 @@ function fit_b200(X_new::Matrix{Float64}, y::Vector{Float64}, R::Integer; η=1.0
     n, q = size(X_new)
     V = Int((-1 + sqrt(1 + 8q)) / 2)
     total = nburn + nsamp
-    p = Ref(BnrParams(n, V, R, num_chains, 0, 0, 1, 1, total, UInt64(seed), η, ζ, ι, aΔ, bΔ, Float64(ν), 64, 0))
+    p = Ref(BnrParams(n, V, R, num_chains, 0, 0, 1, 1, total, UInt64(seed), η, ζ, ι, aΔ, bΔ, Float64(ν), 64, 0, 0, 0))   # gamma_mode = auto, chain_groups = default
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:bnr_create, LIBBNR), Cint, (Ref{BnrParams}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}), p, X_new, y, h))
     try

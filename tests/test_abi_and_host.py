@@ -27,7 +27,7 @@ def test_header_symbols_exported(bnr):
         assert hasattr(lib, name), "libbnr.so does not export " + name
     from bnr_b200 import capi
     assert sorted(capi.PROTOTYPES) == syms, "ctypes prototypes and include/bnr.h disagree"
-    assert bnr.lib().bnr_version() == 100
+    assert bnr.lib().bnr_version() == 101
 
 
 def test_params_struct_matches_header(bnr):
@@ -36,7 +36,8 @@ def test_params_struct_matches_header(bnr):
     bnr.lib().bnr_default_params(ctypes.byref(p))
     assert (p.eta, p.zeta, p.iota, p.a_delta, p.b_delta, p.nu) == (1.01, 1.0, 1.0, 1.0, 1.0, 10.0)
     assert p.num_chains == 2 and p.gig_inject_len == 64 and p.trace_full_chains == 1
-    assert ctypes.sizeof(capi.Params) == 8 * 4 + 8 + 8 + 6 * 8 + 8
+    assert p.gamma_mode == 0 and p.chain_groups == 0
+    assert ctypes.sizeof(capi.Params) == 8 * 4 + 8 + 8 + 6 * 8 + 4 * 4
 
 
 def test_no_gpu_is_a_loud_error(bnr):
