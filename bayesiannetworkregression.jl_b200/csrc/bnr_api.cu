@@ -146,14 +146,16 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   Dims& d = h->e.d;
   d.n = p->n; d.V = p->V; d.R = p->R; d.C = p->num_chains;
   d.q = p->V * (p->V + 1) / 2;
-  d.np = (p->n + TILE_N - 1) / TILE_N * TILE_N;
+  // n is padded to a multiple of 128 with AT LEAST one padding row: row n of the n x n system carries the right-hand
+  // side of the forward solve through the factorisation (bnr_linalg.cu); same for q in the q-form
+  d.np = (p->n + 1 + TILE_N - 1) / TILE_N * TILE_N;
   d.qp = (d.q + TILE_K - 1) / TILE_K * TILE_K;
   // gamma draw formulation (SURVEY 8d cost model): the q x q precision form costs q^3/3 + 4q^2 flops per
   // chain-iteration, the n x n Bhattacharya form (what the reference runs, src/gibbs.jl:429-436) n^2 q + n^3/3.
   {
     const double qd = d.q, nd = d.n;
     const double cost_q = qd * qd * qd / 3.0 + 4.0 * qd * qd, cost_n = nd * nd * qd + nd * nd * nd / 3.0;
-    const int qp128 = (d.q + TILE_N - 1) / TILE_N * TILE_N;
+    const int qp128 = (d.q + 1 + TILE_N - 1) / TILE_N * TILE_N;
     int mode = p->gamma_mode;
     if (mode != BNR_GAMMA_NFORM && mode != BNR_GAMMA_QFORM)
       mode = (cost_q < cost_n && qp128 <= chol_max_dim()) ? BNR_GAMMA_QFORM : BNR_GAMMA_NFORM;
@@ -205,7 +207,7 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   DA(e.W, C * d.qp); DA(e.v, C * d.qp); DA(e.t, C * d.qp);
   DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
   DA(e.G, C * d.gdim * d.gdim + 2048);
-  DA(e.dinv, C * d.gdim);
+  DA(e.Linv, C * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N);
   e.XtX = nullptr;
   if (d.gmode == BNR_GAMMA_QFORM) {
     // X'X once: row-major copy of X as the SYRK operand (k-major over the n samples), unit scales, no identity
@@ -362,7 +364,7 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   v.gamma += c * d.qp; v.S += c * d.qp; v.W += c * d.qp; v.v += c * d.qp; v.t += c * d.qp;
   v.M += c * d.R * d.R; v.lambda += c * d.R; v.pi += c * 3 * d.R;
   v.xg += c * d.np; v.xv += c * d.np; v.rhs += c * d.np;
-  v.G += c * d.gdim * d.gdim; v.dinv += c * d.gdim;
+  v.G += c * d.gdim * d.gdim; v.Linv += c * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N;
   v.partials += c * d.nparts * (2 * MAX_R + 1);
   v.moments += c * 2 * (d.V + d.q) * 2;
   if (v.tr_gx) v.tr_gx += c * v.trace_rows * (d.V + d.q);

@@ -16,7 +16,8 @@ struct Dims {
   int n, V, R, q, C;
   int np, qp;         // padded n (multiple of TILE_N) and q (multiple of TILE_K; of TILE_N in the q-form)
   int gmode;          // gamma draw: 1 = n x n Bhattacharya form (G = X D X' + I), 2 = q x q precision form
-  int gdim;           // dimension of the matrix that is factored every sweep: np (n-form) or qp (q-form)
+  int gdim;           // dimension of the matrix that is factored every sweep: np (n-form) or qp (q-form); always
+                      // > n resp. q: the first padding row carries the right-hand side of the forward solve
   int nparts;         // edge-kernel blocks per chain = ceil(q / PART_BLOCK)
   int chain_offset;
   int gigK;           // injected uniforms per edge
@@ -102,7 +103,7 @@ struct Engine {
   double* xv;       // [C][np]  X (W + delta1)
   double* rhs;      // [C][np]  a1 - a3, then L^-1 rhs, then a4 (in place); q-form: (y - mu - X W)/tau2
   double* G;        // [C][gdim*gdim] col-major, lower triangle used
-  double* dinv;     // [C][gdim]  reciprocal diagonal of the Cholesky factor
+  double* Linv;     // [C][gdim/128][128*128]  inverses of the 128 x 128 diagonal blocks of the factor (column-major)
   double* partials; // [C][nparts][2*MAX_R+1]  block partial sums: A_r, B_r (lambda), sum S
   int* status;      // [C]
   long long* iter;  // device scalar: completed sweeps

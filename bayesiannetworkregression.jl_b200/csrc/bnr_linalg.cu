@@ -1,7 +1,8 @@
 // Dense FP64 linear algebra of the gamma draw (update_gamma!, src/gibbs.jl:420-438), batched over chains:
 //   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, cp.async 3-stage pipeline
-//   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_chol_update (DMMA) / k_potf2_128 / k_trsm_128
-//   a4  = L_c^-T w                    -> k_trsv_bwd128
+//   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_augment / k_chol_update (DMMA) / k_potf2_inv /
+//                                        k_trsm_dmma (DMMA); the forward solve rides along as a bordering row
+//   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
 //   X v, X' a4 (all chains at once)   -> k_x_times (tall-skinny GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
 #include "bnr_engine.cuh"
@@ -225,7 +226,7 @@ __device__ __forceinline__ void syrk_strip_tile(const double* __restrict__ smem,
       const int i = i0 + nf * 8 + 2 * lk;
       double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
       double2 v;
-      if (MODE == 0) {
+      if (MODE != 1) {
         v.x = acc[mf][nf][0];
         v.y = acc[mf][nf][1];
       } else {
@@ -242,7 +243,7 @@ template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
           size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
-          double diag_add) {
+          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0) {
   extern __shared__ __align__(16) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
@@ -266,16 +267,26 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     } else {
       ib = jb = t - noff;
     }
-  } else {
+  } else if (MODE == 1) {
     // left-looking update of block column J = origin: tiles (J+1 .. T-1, J) first, the diagonal tile (J, J) last
     const int T = np / SY_BT, nt = T - origin;
     jb = origin;
     ib = (blockIdx.y == nt - 1) ? origin : origin + 1 + blockIdx.y;
+  } else {
+    // MODE 2: panel solve, tiles (J+1 .. T-1, J)
+    jb = origin;
+    ib = origin + 1 + blockIdx.y;
   }
   const int i0 = ib * SY_BT, j0 = jb * SY_BT;
   const bool diag = (ib == jb);
   const double* Ac = A + (size_t)c * a_chain_stride;
   const double* sc = (MODE == 0) ? scale + (size_t)c * scale_stride : nullptr;
+  // operand sources (k-major: element (row, k) at base[row + ld * k]).  MODE 0 / 1: both operands are row blocks of
+  // the same matrix.  MODE 2: the i operand is block column J of C itself (rows i0.., k = the 128 columns of the
+  // panel), the j operand is the 128 x 128 inverse of the diagonal block (ld = 128, rows 0..127).
+  const double* opj = (MODE == 2) ? Bop + (size_t)c * b_chain_stride : Ac + j0;
+  const double* opi = (MODE == 2) ? Ac + (size_t)j0 * ld + i0 : Ac + i0;
+  const int ldj = (MODE == 2) ? SY_BT : ld;
 
   if (tid == 0) {
     for (int s = 0; s < SY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -295,11 +306,12 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
         double* sj = smem + (size_t)stage * SY_STAGE_DBL;
         double* si = sj + SY_BK * SY_LDS;
         mbar_expect_tx(&full[stage], bytes);
-        const double* g = Ac + (size_t)kt * SY_BK * ld;
+        const double* gj = opj + (size_t)kt * SY_BK * ldj;
+        const double* gi = opi + (size_t)kt * SY_BK * ld;
 #pragma unroll 4
         for (int kr = 0; kr < SY_BK; ++kr) {
-          bulk_g2s(sj + kr * SY_LDS, g + (size_t)kr * ld + j0, SY_BT * 8, &full[stage]);
-          if (!diag) bulk_g2s(si + kr * SY_LDS, g + (size_t)kr * ld + i0, SY_BT * 8, &full[stage]);
+          bulk_g2s(sj + kr * SY_LDS, gj + (size_t)kr * ldj, SY_BT * 8, &full[stage]);
+          if (!diag) bulk_g2s(si + kr * SY_LDS, gi + (size_t)kr * ld, SY_BT * 8, &full[stage]);
         }
         if (MODE == 0) bulk_g2s(si + SY_BK * SY_LDS, sc + kt * SY_BK, SY_BK * 8, &full[stage]);
       }
@@ -331,6 +343,15 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   // are never written by any kernel, so skipping them changes nothing.
   int nfv = (nvalid - i0 + 7) / 8;
   nfv = nfv > 16 ? 16 : nfv;
+  if (nfv <= 0) {
+    // the whole row block is padding: keep the stage hand-shake alive and leave
+    for (int kt = 0; kt < nk; ++kt) {
+      mbar_wait(&full[kt % SY_STAGES], (kt / SY_STAGES) & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[kt % SY_STAGES]);
+    }
+    return;
+  }
   switch (nfv) {
 #define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
     BNR_STRIP_CASE(1) BNR_STRIP_CASE(2) BNR_STRIP_CASE(3) BNR_STRIP_CASE(4) BNR_STRIP_CASE(5) BNR_STRIP_CASE(6)
@@ -353,50 +374,126 @@ k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double*
   syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin, 0.0);
 }
 
+// panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I > J (in place: a CTA has consumed
+// its whole tile through the ring before the first store)
+__global__ void __launch_bounds__(SY_THREADS, 1)
+k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int origin,
+            const double* __restrict__ Linv, size_t linv_chain_stride) {
+  syrk_body<2>(G, chain_stride, np, nullptr, 0, G, chain_stride, np, nvalid, SY_BT / SY_BK, origin, 0.0, Linv,
+               linv_chain_stride);
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// Blocked left-looking Cholesky, block size 128, with the forward solve L w = rhs folded in.
-//   for J = 0 .. np/128-1:
-//     k_chol_update   (DMMA, above):  G[J.., J] -= L[J.., 0:J] L[J, 0:J]'
-//     k_potf2_128     one CTA per chain: factor the 128 x 128 diagonal block in shared
-//                     memory (4 sub-blocks of 32: a warp factors 32 x 32 in registers with shuffles, threads eliminate
-//                     the rows below, everybody updates the trailing part in 2 x 2 register tiles); rhs_J rides along as
-//                     row 128, so w_J = L_JJ^-1 rhs_J comes out of the same elimination.  1/L_jj goes to `dinv`.
-//     k_trsm_128      rows below the diagonal block: L[i, J] = G[i, J] L_JJ^-T, one thread per row, two 64-column
-//                     halves, right-looking inside the thread (independent FMAs, no divisions); the same thread then
-//                     subtracts its row's share of the forward solve: rhs[i] -= L[i, J] w_J.
-// All inner loops are arranged so that consecutive FP64 FMAs are independent: these kernels are latency-bound.
+// Blocked left-looking Cholesky, block size 128, of every chain's gdim x gdim matrix, with BOTH triangular solves
+// organised around it:
+//   * forward solve for free: the right-hand side r is stored as row m (the first padding row, m = n or q) of the
+//     matrix itself, with the diagonal entry d = 1 + |r|^2 / lmin (k_augment; lmin <= lambda_min(G)).  The bordered
+//     matrix [[G, r], [r', d]] is positive definite (r' G^-1 r <= |r|^2 / lambda_min < d), and row m of its Cholesky
+//     factor IS w' = (L^-1 r)': the DMMA update / panel-solve kernels below carry the solve along as one more row of
+//     the last row block.  (The corner entry sqrt(d - |w|^2) is never used.)
+//   * for J = 0 .. T-1:
+//       k_chol_update (DMMA): G[J.., J] -= L[J.., 0:J] L[J, 0:J]'
+//       k_potf2_inv   one CTA per chain: the 128 x 128 diagonal block arrives column-major through the TMA engine,
+//                     is factored in shared memory (32-wide steps: one warp factors 32 x 32 in registers with
+//                     shuffles, a thread per row eliminates below, everybody updates the trailing part in 2 x 2
+//                     register tiles), goes back with bulk stores, and is then INVERTED in place (32 x 32 diagonal
+//                     inverses by substitution, off-diagonal blocks by small products) -> Linv[c][J]
+//       k_trsm_dmma   (DMMA): G[I, J] <- G[I, J] Linv_J' for I > J -- the panel solve is a GEMM
+//   * backward solve L' x = w (+ z): k_bwd_stream, one CTA per chain streams the factor once (bulk copies into a
+//     shared-memory ring, 64-column half blocks), every step is a block mat-vec; the diagonal blocks use Linv.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;            // panel / diagonal block size
-constexpr int PB_LD = PB + 1;      // shared-memory row stride of the (PB+1) x PB working block
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)(PB + 1) * PB_LD + 32);
+constexpr int XD_LD = 34;          // column stride of the 32 x 32 scratch blocks (even: 16-byte loads; 34: spreads banks)
+constexpr int XD_BLK = 32 * XD_LD;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PB + 7 * XD_BLK + PB) + 16;
+constexpr int CHOL_MAX_DIM = 4096; // largest factored dimension (shared-memory solution vector of the back solve)
 
-__global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_t chain_stride, int np, int J,
-                                                   double* __restrict__ rhs, double* __restrict__ dinv_out,
-                                                   int* status) {
-  extern __shared__ double sm[];
-  double* A = sm;                          // A[r][c] at A[r * PB_LD + c], rows 0..128 (row 128 = rhs), cols 0..127
-  double* dinv = sm + (PB + 1) * PB_LD;    // [32] reciprocal diagonal of the current 32-block
-  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// row m of every G_c <- (r_c, 1 + |r_c|^2 / lmin_c), lmin_c a lower bound of the smallest eigenvalue of G_c, so that
+// the bordered matrix stays positive definite (r' G^-1 r <= |r|^2 / lambda_min):  n-form G = X D X' + I: lmin = 1;
+// q-form P = (X'X + D^-1)/tau2: lmin = 1 / (tau2 max_j S_j)  (S, tau2 given).  grid = C, block = 256.
+__global__ void __launch_bounds__(256) k_augment(double* __restrict__ G, size_t chain_stride, int N, int m,
+                                                 const double* __restrict__ r, int r_stride,
+                                                 const double* __restrict__ S, const double* __restrict__ tau2) {
+  __shared__ double red[8], redm[8];
+  const int c = blockIdx.x, tid = threadIdx.x;
   double* Gc = G + (size_t)c * chain_stride;
-  double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
-  double* rc = rhs + (size_t)c * np;
-  const int kprev = J * PB;
-  for (int id = tid; id < PB * PB; id += 256) {
-    const int r = id & (PB - 1), cc = id >> 7;
-    A[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
+  const double* rc = r + (size_t)c * r_stride;
+  double s = 0.0, mx = 0.0;
+  for (int k = tid; k < m; k += 256) {
+    const double v = rc[k];
+    Gc[(size_t)k * N + m] = v;
+    s += v * v;
+    if (S) mx = fmax(mx, S[(size_t)c * r_stride + k]);
   }
-  // rhs rides along as row 128 of the working block; contributions of earlier panels were already subtracted
-  // by k_trsm_128 (right-looking forward solve), so w_J = L_JJ^-1 rhs_J falls out of the elimination below
-  if (tid < PB) A[PB * PB_LD + tid] = rc[kprev + tid];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((tid & 31) == 0) { red[tid >> 5] = s; redm[tid >> 5] = mx; }
   __syncthreads();
+  if (tid == 0) {
+    double t = 0.0, mm = 0.0;
+    for (int w = 0; w < 8; ++w) { t += red[w]; mm = fmax(mm, redm[w]); }
+    const double inv_lmin = S ? tau2[c] * mm : 1.0;
+    Gc[(size_t)m * N + m] = 1.0 + t * inv_lmin;
+  }
+}
+
+// 4 rows x 2 columns of a product of 32 x 32 blocks: acc += Aop[r4 .. r4+3][p] * Bop[p][c2 .. c2+1], p = 0..31
+// (both operands column-major with the given column strides; Aop rows must be 16-byte aligned)
+__device__ __forceinline__ void blk32_fma(double (&acc)[4][2], const double* __restrict__ Aop, int lda,
+                                          const double* __restrict__ Bop, int ldb, int r4, int c2) {
+#pragma unroll 8
+  for (int p = 0; p < 32; ++p) {
+    const double2 a01 = *reinterpret_cast<const double2*>(Aop + p * lda + r4);
+    const double2 a23 = *reinterpret_cast<const double2*>(Aop + p * lda + r4 + 2);
+    const double b0 = Bop[c2 * ldb + p], b1 = Bop[(c2 + 1) * ldb + p];
+    acc[0][0] += a01.x * b0; acc[0][1] += a01.x * b1;
+    acc[1][0] += a01.y * b0; acc[1][1] += a01.y * b1;
+    acc[2][0] += a23.x * b0; acc[2][1] += a23.x * b1;
+    acc[3][0] += a23.y * b0; acc[3][1] += a23.y * b1;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_t chain_stride, int N, int J,
+                                                   double* __restrict__ Linv, int T, int* status) {
+  extern __shared__ __align__(16) double sm[];
+  double* A = sm;                          // column-major 128 x 128 working block: A[col * PB + row]
+  double* Xd = sm + PB * PB;               // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
+  double* Tm = Xd + 4 * XD_BLK;            // [3] products of the off-diagonal stage
+  double* dall = Tm + 3 * XD_BLK;          // [128] reciprocal diagonal of L
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(dall + PB);
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* D = G + (size_t)c * chain_stride + (size_t)J * PB * N + (size_t)J * PB;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, PB * PB * 8);
+    for (int col = 0; col < PB; ++col) bulk_g2s(A + col * PB, D + (size_t)col * N, PB * 8, bar);
+  }
+  mbar_wait(bar, 0);
   bool bad = false;
   for (int s = 0; s < PB / 32; ++s) {
     const int o = s * 32;
     if (warp == 0) {
-      // 32 x 32 Cholesky in registers: lane r holds row o+r (columns o .. o+31)
+      // 32 x 32 Cholesky in registers: lane r holds row o+r (columns o .. o+31); entries above the diagonal are
+      // whatever the block held there and never reach a valid entry
       double a[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = A[(o + lane) * PB_LD + o + j];
+      for (int j = 0; j < 32; ++j) a[j] = A[(o + j) * PB + o + lane];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const double djj = __shfl_sync(0xffffffffu, a[j], j);
@@ -404,237 +501,234 @@ __global__ void __launch_bounds__(256) k_potf2_128(double* __restrict__ G, size_
         const double inv = rsqrt(djj);
         const double lj = (lane == j) ? djj * inv : a[j] * inv;
         a[j] = lj;
-        if (lane == j) dinv[j] = inv;
+        if (lane == j) dall[o + j] = inv;
 #pragma unroll
         for (int cc = j + 1; cc < 32; ++cc) {
           const double lcj = __shfl_sync(0xffffffffu, lj, cc);
-          a[cc] -= lj * lcj;                 // lanes < cc compute garbage in their (unused) upper part
+          a[cc] -= lj * lcj;
         }
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (lane >= j) A[(o + lane) * PB_LD + o + j] = a[j];
+        if (lane >= j) A[(o + j) * PB + o + lane] = a[j];
     }
     __syncthreads();
-    // rows below (incl. the rhs row 128): x L_ss' = a, thread per row, right-looking (independent FMAs)
-    const int nbelow = PB + 1 - (o + 32);
+    // rows below: x L_ss' = a, thread per row, right-looking (independent FMAs, broadcast reads of L_ss)
+    const int nbelow = PB - (o + 32);
     if (tid < nbelow) {
-      double* row = A + (o + 32 + tid) * PB_LD + o;
+      double* row = A + o * PB + o + 32 + tid;
       double x[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = row[j];
+      for (int j = 0; j < 32; ++j) x[j] = row[j * PB];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const double xj = x[j] * dinv[j];
+        const double xj = x[j] * dall[o + j];
         x[j] = xj;
 #pragma unroll
-        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + k) * PB_LD + o + j];
+        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PB + o + k];
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) row[j] = x[j];
+      for (int j = 0; j < 32; ++j) row[j * PB] = x[j];
     }
     __syncthreads();
-    // trailing update inside the block in 2 x 2 register tiles:
-    //   A[r][cc] -= sum_p L[r][o+p] L[cc][o+p],  o+32 <= cc <= r <= 128 (cc < 128)
+    // trailing update in 2 x 2 register tiles: A[r][cc] -= sum_p L[r][o+p] L[cc][o+p], o+32 <= cc <= r
     const int base = o + 32;
-    const int nr2 = (PB + 1 - base + 1) / 2;     // row pairs (rows base .. 128)
-    const int nc2 = (PB - base) / 2;             // column pairs (cols base .. 127), even count
-    for (int id = tid; id < nr2 * nc2; id += 256) {
-      const int r = base + 2 * (id / nc2), cc = base + 2 * (id % nc2);
-      if (cc > r + 1) continue;
-      const int r1 = (r + 1 <= PB) ? r + 1 : r;  // clamp the phantom row 129
-      const double* La = A + r * PB_LD + o;
-      const double* Lb = A + r1 * PB_LD + o;
-      const double* Lc = A + cc * PB_LD + o;
-      const double* Ld = A + (cc + 1) * PB_LD + o;
+    const int n2 = (PB - base) / 2;              // row / column pairs
+    for (int id = tid; id < n2 * n2; id += 256) {
+      const int r = base + 2 * (id % n2), cc = base + 2 * (id / n2);
+      if (cc > r) continue;
       double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll
+#pragma unroll 8
       for (int p = 0; p < 32; ++p) {
-        const double la = La[p], lb = Lb[p], lc = Lc[p], ld = Ld[p];
-        s00 += la * lc; s01 += la * ld; s10 += lb * lc; s11 += lb * ld;
+        const double2 lr2 = *reinterpret_cast<const double2*>(A + (o + p) * PB + r);
+        const double2 lc2 = *reinterpret_cast<const double2*>(A + (o + p) * PB + cc);
+        s00 += lr2.x * lc2.x; s01 += lr2.x * lc2.y; s10 += lr2.y * lc2.x; s11 += lr2.y * lc2.y;
       }
-      A[r * PB_LD + cc] -= s00;
-      if (cc + 1 <= r) A[r * PB_LD + cc + 1] -= s01;
-      if (r1 != r) {
-        A[r1 * PB_LD + cc] -= s10;
-        A[r1 * PB_LD + cc + 1] -= s11;
-      }
+      double2* p0 = reinterpret_cast<double2*>(A + cc * PB + r);
+      double2 v = *p0;
+      v.x -= s00; v.y -= s10;
+      *p0 = v;
+      double2* p1 = reinterpret_cast<double2*>(A + (cc + 1) * PB + r);
+      v = *p1;
+      if (cc + 1 <= r) v.x -= s01;
+      v.y -= s11;
+      *p1 = v;
     }
     __syncthreads();
-    if (tid < 32) dinv_out[(size_t)c * np + kprev + o + tid] = dinv[tid];
   }
   if (bad) atomicOr(&status[c], BNR_ST_G_NOTPD_);
+  // the factor goes back to global memory (full columns: the part above the diagonal is never read by anyone)
+  fence_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    for (int col = 0; col < PB; ++col) bulk_s2g(D + (size_t)col * N, A + col * PB, PB * 8);
+    bulk_commit();
+    bulk_wait_read0();
+  }
+  // ---- inverse, in place ----
+  // (1) the four 32 x 32 diagonal inverses, thread per column: x = e_j, forward substitution in registers
+  if (tid < 128) {
+    const int b = tid >> 5, j = tid & 31, o = 32 * b;
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const double xk = x[k] * dall[o + k];
+      x[k] = xk;
+#pragma unroll
+      for (int i = k + 1; i < 32; ++i) x[i] -= A[(o + k) * PB + o + i] * xk;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Xd[b * XD_BLK + j * XD_LD + i] = (i >= j) ? x[i] : 0.0;
+  }
+  __syncthreads();   // also orders the bulk-store reads (tid 0 waited above) before the in-place overwrite below
+  // (2) block columns from the right: X_ij = -(sum_{k=j+1..i} X_ik L_kj) X_jj for i = j+1 .. 3; X_ik (k > j) is
+  //     final, L_kj (column j) is still the factor because column j is overwritten only at the end of its step
+  for (int j = 2; j >= 0; --j) {
+    const int nb = 3 - j;
+    for (int t = tid; t < nb * 128; t += 256) {
+      const int bi = t >> 7, i = j + 1 + bi, tt = t & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
+      double acc[4][2] = {};
+      for (int k = j + 1; k <= i; ++k) {
+        const double* Lkj = A + (32 * j) * PB + 32 * k;
+        if (k == i) blk32_fma(acc, Xd + i * XD_BLK, XD_LD, Lkj, PB, r4, c2);
+        else blk32_fma(acc, A + (32 * k) * PB + 32 * i, PB, Lkj, PB, r4, c2);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        Tm[bi * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
+        Tm[bi * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < nb * 128; t += 256) {
+      const int bi = t >> 7, i = j + 1 + bi, tt = t & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
+      double acc[4][2] = {};
+      blk32_fma(acc, Tm + bi * XD_BLK, XD_LD, Xd + j * XD_BLK, XD_LD, r4, c2);
+      double* dst = A + (32 * j + c2) * PB + 32 * i + r4;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { dst[a] = -acc[a][0]; dst[PB + a] = -acc[a][1]; }
+    }
+    __syncthreads();
+  }
+  // (3) diagonal blocks from Xd, exact zeros above the diagonal (the panel solve sums over all 128 k)
   for (int id = tid; id < PB * PB; id += 256) {
     const int r = id & (PB - 1), cc = id >> 7;
-    if (r >= cc) D[(size_t)cc * np + r] = A[r * PB_LD + cc];
+    if (r < cc) A[id] = 0.0;
+    else if ((r >> 5) == (cc >> 5)) A[id] = Xd[(r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31)];
   }
-  if (tid < PB) rc[kprev + tid] = A[PB * PB_LD + tid];
-}
-
-// rows below the diagonal block.  grid = (rows_below / 128, C), block = 128.
-// shared: Lt11, Lt21, Lt22 as [p][j] (column p of the 64 x 64 sub-block contiguous in j, read as 16-byte broadcasts),
-// 128 reciprocal diagonals and w_J.
-constexpr size_t TRSM_SMEM = sizeof(double) * (3 * 64 * 64 + 256);
-
-// x[k] -= xj * l[k] for k = K0 .. 63 with 16-byte shared loads (K0 is a compile-time constant)
-template <int K0>
-__device__ __forceinline__ void axpy_tail(double (&x)[64], double xj, const double* __restrict__ l) {
-  constexpr int KE = (K0 + 1) & ~1;                    // first even index >= K0
-  if (K0 & 1) x[K0] -= xj * l[K0];
-  const double2* lv = reinterpret_cast<const double2*>(l);
-#pragma unroll
-  for (int k2 = KE / 2; k2 < 32; ++k2) {
-    const double2 v = lv[k2];
-    x[2 * k2] -= xj * v.x;
-    x[2 * k2 + 1] -= xj * v.y;
-  }
-}
-
-template <int J0>
-__device__ __forceinline__ void trsm_solve64(double (&x)[64], const double* __restrict__ Lt, const double* __restrict__ dinv) {
-  if constexpr (J0 < 64) {
-    const double xj = x[J0] * dinv[J0];
-    x[J0] = xj;
-    if constexpr (J0 + 1 < 64) axpy_tail<J0 + 1>(x, xj, Lt + J0 * 64);
-    trsm_solve64<J0 + 1>(x, Lt, dinv);
-  }
-}
-
-__global__ void __launch_bounds__(128) k_trsm_128(double* __restrict__ G, size_t chain_stride, int np, int J,
-                                                  const double* __restrict__ dinv_g, double* __restrict__ rhs) {
-  extern __shared__ __align__(16) double sm[];
-  double* L11 = sm;                 // [p][j] = L11[j][p]
-  double* L21 = sm + 64 * 64;       // [p][j] = L21[j][p]   (j: second-half column, p: first-half column)
-  double* L22 = sm + 2 * 64 * 64;
-  double* dinv = sm + 3 * 64 * 64;  // [128]
-  double* wJ = dinv + 128;          // [128]
-  const int c = blockIdx.y, tid = threadIdx.x;
-  double* Gc = G + (size_t)c * chain_stride;
-  const double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
-  for (int id = tid; id < 64 * 64; id += 128) {
-    const int r = id & 63, cc = id >> 6;          // D(r, cc) column-major: coalesced in r
-    L11[cc * 64 + r] = D[(size_t)cc * np + r];
-    L21[cc * 64 + r] = D[(size_t)cc * np + 64 + r];
-    L22[cc * 64 + r] = D[(size_t)(64 + cc) * np + 64 + r];
-  }
-  dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
-  wJ[tid] = rhs[(size_t)c * np + J * PB + tid];
+  fence_async_smem();
   __syncthreads();
-  const int row = (J + 1) * PB + blockIdx.x * 128 + tid;
-  if (row >= np) return;
-  double* prow = Gc + (size_t)J * PB * np + row;
-  double* prow2 = prow + (size_t)64 * np;
-  double x[64];
-#pragma unroll
-  for (int j = 0; j < 64; ++j) x[j] = prow[(size_t)j * np];
-  trsm_solve64<0>(x, L11, dinv);            // first half: x_j = a_j / L11[j][j]; a_k -= x_j L11[k][j] (k > j)
-  double racc = 0.0;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { prow[(size_t)j * np] = x[j]; racc += x[j] * wJ[j]; }
-  // second half, 16 columns at a time: y_k = A[row][64 + k] - sum_p x_p L21[k][p]
-#pragma unroll 1
-  for (int k0 = 0; k0 < 64; k0 += 16) {
-    double y[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) y[k] = prow2[(size_t)(k0 + k) * np];
-#pragma unroll
-    for (int p = 0; p < 64; ++p) {
-      const double2* l2 = reinterpret_cast<const double2*>(L21 + p * 64 + k0);
-#pragma unroll
-      for (int k2 = 0; k2 < 8; ++k2) {
-        const double2 v = l2[k2];
-        y[2 * k2] -= x[p] * v.x;
-        y[2 * k2 + 1] -= x[p] * v.y;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) prow2[(size_t)(k0 + k) * np] = y[k];
+  if (tid == 0) {
+    double* dst = Linv + ((size_t)c * T + J) * PB * PB;
+    for (int col = 0; col < PB; ++col) bulk_s2g(dst + col * PB, A + col * PB, PB * 8);
+    bulk_commit();
+    bulk_wait0();
   }
-#pragma unroll
-  for (int j = 0; j < 64; ++j) x[j] = prow2[(size_t)j * np];
-  trsm_solve64<0>(x, L22, dinv + 64);
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { prow2[(size_t)j * np] = x[j]; racc += x[j] * wJ[64 + j]; }
-  // right-looking forward solve: this row's right-hand side loses the contribution of panel J
-  rhs[(size_t)c * np + row] -= racc;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward solve  L' x = w  (w in rhs, overwritten by x), left-looking over 128-blocks from the bottom.
-// grid = C, block = 256 (8 warps): warp per column group for the matvec with the rows below (coalesced, 8 columns in
-// flight per warp), then a 128 x 128 transposed triangular solve by one warp (shuffles, reciprocal diagonals).
+// backward solve  L' x = b,  b = w (+ addz), w = row m of the factor (see above).  One CTA per chain; a producer
+// warp streams the factor once, bottom-right to top-left, as 64-column half blocks (64 bulk copies of 1 KB) into a
+// ring; 8 consumer warps turn every half block into 64 dot products (warp per 8 columns, lanes over the rows):
+//   off-diagonal block (I, J): b_J -= L[I, J]' x_I          diagonal block J: x_J = Linv_J' b_J
+// grid = C, block = 288 (8 consumer warps + 1 producer warp).
 // ------------------------------------------------------------------------------------------------------------
-static size_t trsvb_smem(int np) { return sizeof(double) * ((size_t)PB * PB_LD + np + 2 * PB); }
-constexpr int CHOL_MAX_DIM = 4096;   // largest factored dimension (shared-memory solution vector of the back solve)
+constexpr int BW_COLS = 64;
+constexpr int BW_STAGE_DBL = BW_COLS * PB;
+static int bwd_stages(int N) {
+  const size_t budget = 227 * 1024 - sizeof(double) * (size_t)N - 256;
+  int ns = (int)(budget / (sizeof(double) * BW_STAGE_DBL));
+  return ns > 3 ? 3 : ns;
+}
+static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 128; }
 
-// addz (optional, [C][np]): added to the right-hand side before the solve - the q-form draws L' beta = w + z
-__global__ void __launch_bounds__(256) k_trsv_bwd128(const double* __restrict__ G, size_t chain_stride, int np,
-                                                     double* __restrict__ rhs, const double* __restrict__ dinv_g,
-                                                     const double* __restrict__ addz) {
-  extern __shared__ double sm[];
-  double* Ls = sm;                     // [r][c] lower block
-  double* x = sm + PB * PB_LD;         // [np] solution so far (entries >= (J+1)*128 valid)
-  double* b = x + np;                  // [128] current right-hand side
-  double* dinv = b + PB;               // [128]
+__global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G, size_t chain_stride, int N, int m,
+                                                    const double* __restrict__ Linv, double* __restrict__ out,
+                                                    int out_stride, const double* __restrict__ addz, int addz_stride,
+                                                    int nstages) {
+  extern __shared__ __align__(16) double sm[];
+  double* ring = sm;
+  double* x = sm + (size_t)nstages * BW_STAGE_DBL;     // [N] right-hand side, overwritten block by block by x
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(x + N);
+  unsigned long long* empty = full + 4;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = N / PB;
   const double* Gc = G + (size_t)c * chain_stride;
-  double* rc = rhs + (size_t)c * np;
-  const int T = np / PB;
-  for (int J = T - 1; J >= 0; --J) {
-    const int r0 = (J + 1) * PB, nrow = np - r0;
-    const double* D = Gc + (size_t)J * PB * np + (size_t)J * PB;
-    for (int id = tid; id < PB * PB; id += 256) {
-      const int r = id & (PB - 1), cc = id >> 7;
-      Ls[r * PB_LD + cc] = (r >= cc) ? D[(size_t)cc * np + r] : 0.0;
-    }
-    if (tid < PB) dinv[tid] = dinv_g[(size_t)c * np + J * PB + tid];
-    // b_j = w_j - sum_{i >= r0} L[i][J*128 + j] x_i : warp w owns columns 16w .. 16w+15, all 16 in flight
-    {
-      const int jj = warp * 16;
-      double acc[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) acc[u] = 0.0;
-      const double* col = Gc + (size_t)(J * PB + jj) * np + r0;
-      for (int i = lane; i < nrow; i += 32) {
-        const double xi = x[r0 + i];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) acc[u] += col[(size_t)u * np + i] * xi;
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        double v = acc[u];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-          const int idx = J * PB + jj + u;
-          b[jj + u] = rc[idx] + (addz ? addz[(size_t)c * np + idx] : 0.0) - v;
-        }
-      }
-    }
-    __syncthreads();
-    // L_JJ' x_J = b : columns from the right; one warp, lane owns entries lane, lane+32, lane+64, lane+96
-    if (warp == 0) {
-      double v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = b[lane + 32 * u];
-#pragma unroll
-      for (int u = 3; u >= 0; --u) {
-        for (int src = 31; src >= 0; --src) {
-          const int j = 32 * u + src;
-          const double xj = __shfl_sync(0xffffffffu, v[u], src) * dinv[j];
-          const double* Lj = Ls + j * PB_LD;
-          if (lane == src) v[u] = xj;
-          else if (lane < src) v[u] -= Lj[lane + 32 * u] * xj;
-#pragma unroll
-          for (int uu = 0; uu < 4; ++uu)
-            if (uu < u) v[uu] -= Lj[lane + 32 * uu] * xj;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { x[J * PB + lane + 32 * u] = v[u]; rc[J * PB + lane + 32 * u] = v[u]; }
-    }
-    __syncthreads();
+  const double* Lc = Linv + (size_t)c * T * PB * PB;
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  for (int k = tid; k < N; k += blockDim.x)
+    x[k] = (k < m) ? Gc[(size_t)k * N + m] + (addz ? addz[(size_t)c * addz_stride + k] : 0.0) : 0.0;
+  __syncthreads();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int it = 0;
+      for (int J = T - 1; J >= 0; --J)
+        for (int I = T - 1; I >= J; --I)            // I == J: the diagonal block, taken from Linv, comes last
+          for (int h = 0; h < 2; ++h, ++it) {
+            const int stage = it % nstages;
+            mbar_wait(&empty[stage], ((it / nstages) & 1) ^ 1);
+            double* dst = ring + (size_t)stage * BW_STAGE_DBL;
+            mbar_expect_tx(&full[stage], BW_STAGE_DBL * 8);
+            const double* src = (I == J) ? Lc + (size_t)J * PB * PB + (size_t)h * BW_COLS * PB
+                                         : Gc + (size_t)(J * PB + h * BW_COLS) * N + (size_t)I * PB;
+            const size_t cs = (I == J) ? PB : N;
+#pragma unroll 4
+            for (int col = 0; col < BW_COLS; ++col) bulk_g2s(dst + col * PB, src + col * cs, PB * 8, &full[stage]);
+          }
+    }
+    return;
+  }
+
+  int it = 0;
+  double xn[2][8];                                   // diagonal-block results of this warp's columns (both halves)
+  for (int J = T - 1; J >= 0; --J) {
+    for (int I = T - 1; I >= J; --I) {
+      const bool dg = (I == J);
+      if (dg) asm volatile("bar.sync 1, 256;\n" ::: "memory");     // b_J complete (all warps' updates landed)
+      const double* v = x + I * PB;
+      const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+#pragma unroll
+      for (int h = 0; h < 2; ++h, ++it) {
+        const int stage = it % nstages;
+        mbar_wait(&full[stage], (it / nstages) & 1);
+        const double* B = ring + (size_t)stage * BW_STAGE_DBL + (size_t)(warp * 8) * PB + lane;
+        double acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          acc[q] = B[q * PB] * v0 + B[q * PB + 32] * v1 + B[q * PB + 64] * v2 + B[q * PB + 96] * v3;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        }
+        if (dg) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xn[h][q] = acc[q];
+        } else if (lane == 0) {
+          double* bj = x + J * PB + h * BW_COLS + warp * 8;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bj[q] -= acc[q];
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");               // everybody has read b_J
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[J * PB + h * BW_COLS + warp * 8 + q] = xn[h][q];
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");               // x_J visible to the next block column
+  }
+  for (int k = tid; k < N; k += 256) out[(size_t)c * out_stride + k] = x[k];
 }
 
 // symmetric copy of G (lower -> full) into the aux buffer, for the parity tests.  grid = (np, C)
@@ -754,9 +848,9 @@ void launch_x_times(const Engine& e, int trans, const double* in, double* out, d
 void linalg_setup() {
   cudaFuncSetAttribute(k_gram_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
-  cudaFuncSetAttribute(k_potf2_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
-  cudaFuncSetAttribute(k_trsm_128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
-  cudaFuncSetAttribute(k_trsv_bwd128, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsvb_smem(CHOL_MAX_DIM));
+  cudaFuncSetAttribute(k_trsm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
+  cudaFuncSetAttribute(k_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
+  cudaFuncSetAttribute(k_bwd_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 void launch_syrk_G(const Engine& e, cudaStream_t s) {
@@ -822,31 +916,36 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
   }
 }
 
-// factor every G_c (gdim x gdim) in place AND forward-solve: rhs_c <- L_c^-1 rhs_c
+// factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix
 void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
-  const int nvalid = d.gmode == 2 ? d.q : d.n;    // rows beyond are identity padding: exact zeros off the diagonal
+  const int m = d.gmode == 2 ? d.q : d.n;         // first padding row = the bordering row
   const size_t cs = (size_t)N * N;
   const int T = N / PB;
+  ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
   for (int J = 0; J < T; ++J) {
     if (J > 0) {
       dim3 g2(d.C, T - J);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, nvalid, J * PB / SY_BK, J);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, J * PB / SY_BK, J);
     }
-    ++g_launches; k_potf2_128<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, rhs, e.dinv, e.status);
+    ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status);
     if (J + 1 < T) {
-      dim3 g1(T - J - 1, d.C);
-      ++g_launches; k_trsm_128<<<g1, 128, TRSM_SMEM, s>>>(e.G, cs, N, J, e.dinv, rhs);
+      dim3 g1(d.C, T - J - 1);
+      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, e.Linv + (size_t)J * PB * PB,
+                                                              (size_t)T * PB * PB);
     }
   }
 }
 
-// rhs_c <- L_c^-T (rhs_c + addz_c)  (the forward half already happened inside launch_cholesky)
-void launch_chol_solve(const Engine& e, double* rhs, const double* addz, cudaStream_t s) {
+// out_c <- L_c^-T (w_c + addz_c), w = L^-1 rhs = row m of the factor (launch_cholesky)
+void launch_chol_solve(const Engine& e, double* out, const double* addz, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
-  ++g_launches; k_trsv_bwd128<<<d.C, 256, trsvb_smem(N), s>>>(e.G, (size_t)N * N, N, rhs, e.dinv, addz);
+  const int m = d.gmode == 2 ? d.q : d.n;
+  const int stride = d.gmode == 2 ? d.qp : d.np;
+  ++g_launches; k_bwd_stream<<<d.C, 288, bwd_smem(N), s>>>(e.G, (size_t)N * N, N, m, e.Linv, out, stride, addz, stride,
+                                                        bwd_stages(N));
 }
 
 int chol_max_dim() { return CHOL_MAX_DIM; }
