@@ -3,7 +3,7 @@
 //   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_augment / k_chol_update (DMMA) / k_potf2_inv /
 //                                        k_trsm_dmma (DMMA); the forward solve rides along as a bordering row
 //   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
-//   X v, X' a4 (all chains at once)   -> k_x_times (tall-skinny GEMM, deterministic split-K)
+//   X v, X' a4 (all chains at once)   -> k_xmma (tall-skinny DMMA GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
 #include "bnr_engine.cuh"
 #include "bnr_kernels.h"
@@ -743,63 +743,110 @@ __global__ void k_copy_sym(const double* __restrict__ G, size_t chain_stride, in
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// tall-skinny GEMM with X for all chains at once: out[c][m] = sum_k A(m,k) in[c][k]
+// tall-skinny GEMM with X for all chains at once on the FP64 tensor cores: out[c][m] = sum_k A(m,k) in[c][k]
 //   TRANS = 0: A(m,k) = X[m + np*k]  (M = np, K = qp)      TRANS = 1: A(m,k) = X[k + np*m]  (M = qp, K = np)
-// 64 x 32 x 16 tiles, 256 threads, 4 x 2 per thread, deterministic split-K through a workspace.
+// CTA tile 128 (m) x 64 (chains), k-step 16, 3-stage cp.async pipeline, 8 warps as 4 (m) x 2 (chains), warp tile
+// 32 x 32 = 4 x 4 DMMA m8n8k4 per k4-step.  K is split over gridDim.z (deterministic: partial sums go to a
+// workspace and are added in a fixed order by k_splitk_reduce) so that ~2 waves of CTAs stream X exactly once.
+// Shared tiles: X as [k][m] (ld 132) for TRANS 0 / [m][k] (ld 20) for TRANS 1, the vectors as [chain][k] (ld 20);
+// both strides are == 4 mod 16 doubles, which makes the (row, k) fragment loads bank-conflict free.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int XT_BM = 64, XT_BN = 32, XT_BK = 16;
+constexpr int XM_BM = 128, XM_BN = 64, XM_BK = 16, XM_STAGES = 3;
+constexpr int XM_LDM = 132, XM_LDK = 20;
+constexpr int XM_A_DBL = (XM_BK * XM_LDM > XM_BM * XM_LDK) ? XM_BK * XM_LDM : XM_BM * XM_LDK;   // 2560
+constexpr int XM_STAGE_DBL = XM_A_DBL + XM_BN * XM_LDK;
+constexpr size_t XMMA_SMEM = sizeof(double) * XM_STAGES * XM_STAGE_DBL;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(sz));
+}
 
 template <int TRANS>
-__global__ void __launch_bounds__(256) k_x_times(const double* __restrict__ X, int np, int M, int K, int N,
-                                                 const double* __restrict__ in, int ldin, double* __restrict__ out,
-                                                 int ldout, int k_per_split) {
-  __shared__ double As[XT_BK][XT_BM + 4];
-  __shared__ double Bs[XT_BK][XT_BN + 2];
-  const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * XT_BM, n0 = blockIdx.y * XT_BN;
+__global__ void __launch_bounds__(256) k_xmma(const double* __restrict__ X, int np, int M, int K, int N,
+                                              const double* __restrict__ in, int ldin, double* __restrict__ out,
+                                              int ldout, int k_per_split) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lk = lane & 3, lr = lane >> 2, wm = warp & 3, wn = warp >> 2;
+  const int m0 = blockIdx.x * XM_BM, n0 = blockIdx.y * XM_BN;
   const int kbeg = blockIdx.z * k_per_split;
   const int kend = min(K, kbeg + k_per_split);
+  const int nsteps = (kend - kbeg + XM_BK - 1) / XM_BK;
   double* o = out + (size_t)blockIdx.z * N * ldout;
-  const int tx = tid & 15, ty = tid >> 4;
-  double acc[4][2] = {};
-  for (int k0 = kbeg; k0 < kend; k0 += XT_BK) {
+
+  auto load_stage = [&](int step) {
+    double* As = sm + (size_t)(step % XM_STAGES) * XM_STAGE_DBL;
+    double* Vs = As + XM_A_DBL;
+    const int k0 = kbeg + step * XM_BK;
+    if (TRANS == 0) {
+      // 16 k-rows of 128 contiguous m: 64 x 16-byte pieces per row
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int id = tid + 256 * r;
-      if (TRANS == 0) {
-        const int kk = id >> 6, mm = id & 63;
-        As[kk][mm] = (m0 + mm < M) ? X[(size_t)(k0 + kk) * np + m0 + mm] : 0.0;
-      } else {
-        const int mm = id >> 4, kk = id & 15;
-        As[kk][mm] = (m0 + mm < M) ? X[(size_t)(m0 + mm) * np + k0 + kk] : 0.0;
+      for (int r = 0; r < 4; ++r) {
+        const int id = tid + 256 * r, kk = id >> 6, mm = (id & 63) * 2;
+        cp_async16_zfill(As + kk * XM_LDM + mm, X + (size_t)(k0 + kk) * np + m0 + mm, m0 + mm < M);
+      }
+    } else {
+      // 128 m-rows of 16 contiguous k: 8 x 16-byte pieces per row
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int id = tid + 256 * r, mm = id >> 3, kk = (id & 7) * 2;
+        const bool ok = m0 + mm < M;
+        cp_async16_zfill(As + mm * XM_LDK + kk, X + (size_t)(ok ? m0 + mm : 0) * np + k0 + kk, ok);
       }
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const int id = tid + 256 * r;
-      const int nn = id >> 4, kk = id & 15;
-      Bs[kk][nn] = (n0 + nn < N) ? in[(size_t)(n0 + nn) * ldin + k0 + kk] : 0.0;
+      const int id = tid + 256 * r, nn = id >> 3, kk = (id & 7) * 2;
+      const bool ok = n0 + nn < N;
+      cp_async16_zfill(Vs + nn * XM_LDK + kk, in + (size_t)(ok ? n0 + nn : 0) * ldin + k0 + kk, ok);
     }
-    __syncthreads();
+  };
+
+  double acc[4][4][2];
 #pragma unroll
-    for (int kk = 0; kk < XT_BK; ++kk) {
-      double a[4], b[2];
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
-      b[0] = Bs[kk][ty * 2]; b[1] = Bs[kk][ty * 2 + 1];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { acc[i][0] += a[i] * b[0]; acc[i][1] += a[i] * b[1]; }
-    }
-    __syncthreads();
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  for (int s = 0; s < XM_STAGES - 1; ++s) {
+    if (s < nsteps) load_stage(s);
+    cp_async_commit();
   }
+  for (int step = 0; step < nsteps; ++step) {
+    cp_async_wait<XM_STAGES - 2>();
+    __syncthreads();
+    if (step + XM_STAGES - 1 < nsteps) load_stage(step + XM_STAGES - 1);
+    cp_async_commit();
+    const double* As = sm + (size_t)(step % XM_STAGES) * XM_STAGE_DBL;
+    const double* Vs = As + XM_A_DBL;
 #pragma unroll
-  for (int jn = 0; jn < 2; ++jn) {
-    const int nn = n0 + ty * 2 + jn;
-    if (nn >= N) continue;
+    for (int k4 = 0; k4 < XM_BK / 4; ++k4) {
+      const int kr = k4 * 4 + lk;
+      double af[4], bf[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int mm = m0 + tx * 4 + i;
-      if (mm < M) o[(size_t)nn * ldout + mm] = acc[i][jn];
+      for (int mf = 0; mf < 4; ++mf)
+        af[mf] = (TRANS == 0) ? As[kr * XM_LDM + wm * 32 + mf * 8 + lr] : As[(wm * 32 + mf * 8 + lr) * XM_LDK + kr];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) bf[nf] = Vs[(wn * 32 + nf * 8 + lr) * XM_LDK + kr];
+#pragma unroll
+      for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int mf = 0; mf < 4; ++mf) {
+    const int mm = m0 + wm * 32 + mf * 8 + lr;
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) {
+      const int nn = n0 + wn * 32 + nf * 8 + 2 * lk;
+      if (mm < M) {
+        if (nn < N) o[(size_t)nn * ldout + mm] = acc[mf][nf][0];
+        if (nn + 1 < N) o[(size_t)(nn + 1) * ldout + mm] = acc[mf][nf][1];
+      }
     }
   }
 }
@@ -814,11 +861,11 @@ __global__ void k_splitk_reduce(const double* __restrict__ ws, double* __restric
 
 static int x_times_splits(const Dims& d, int trans) {
   const int M = trans ? d.qp : d.np, K = trans ? d.np : d.qp;
-  const int tiles = ((M + XT_BM - 1) / XT_BM) * ((d.C + XT_BN - 1) / XT_BN);
+  const int tiles = ((M + XM_BM - 1) / XM_BM) * ((d.C + XM_BN - 1) / XM_BN);
   int ks = (2 * 148 + tiles - 1) / tiles;
-  const int kmax = K / (4 * XT_BK) > 0 ? K / (4 * XT_BK) : 1;
+  const int kmax = K / (4 * XM_BK) > 0 ? K / (4 * XM_BK) : 1;
   if (ks > kmax) ks = kmax;
-  if (ks > 32) ks = 32;
+  if (ks > 64) ks = 64;
   if (ks < 1) ks = 1;
   return ks;
 }
@@ -834,11 +881,12 @@ void launch_x_times(const Engine& e, int trans, const double* in, double* out, d
   const int M = trans ? d.qp : d.np, K = trans ? d.np : d.qp, N = d.C;
   const int ldin = trans ? d.np : d.qp, ldout = trans ? d.qp : d.np;
   const int ks = x_times_splits(d, trans);
-  int kper = ((K + ks - 1) / ks + XT_BK - 1) / XT_BK * XT_BK;
-  dim3 grid((M + XT_BM - 1) / XT_BM, (N + XT_BN - 1) / XT_BN, ks);
+  const int kper = ((K + ks - 1) / ks + XM_BK - 1) / XM_BK * XM_BK;
+  dim3 grid((M + XM_BM - 1) / XM_BM, (N + XM_BN - 1) / XM_BN, ks);
   double* dst = ks == 1 ? out : ws;
-  if (trans) k_x_times<1><<<grid, 256, 0, s>>>(e.X, d.np, M, K, N, in, ldin, dst, ldout, kper);
-  else k_x_times<0><<<grid, 256, 0, s>>>(e.X, d.np, M, K, N, in, ldin, dst, ldout, kper);
+  ++g_launches;
+  if (trans) k_xmma<1><<<grid, 256, XMMA_SMEM, s>>>(e.X, d.np, M, K, N, in, ldin, dst, ldout, kper);
+  else k_xmma<0><<<grid, 256, XMMA_SMEM, s>>>(e.X, d.np, M, K, N, in, ldin, dst, ldout, kper);
   if (ks > 1) {
     const size_t count = (size_t)N * ldout;
     ++g_launches; k_splitk_reduce<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(ws, out, count, ks);
@@ -846,6 +894,8 @@ void launch_x_times(const Engine& e, int trans, const double* in, double* out, d
 }
 
 void linalg_setup() {
+  cudaFuncSetAttribute(k_xmma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XMMA_SMEM);
+  cudaFuncSetAttribute(k_xmma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XMMA_SMEM);
   cudaFuncSetAttribute(k_gram_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   cudaFuncSetAttribute(k_trsm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
