@@ -43,6 +43,7 @@ struct ChainGroup {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   cudaEvent_t done = nullptr;
+  ForkJoin fj;                   // side stream of the Cholesky (off-diagonal panel updates)
   double* ws = nullptr;          // split-K workspace of this group
   long long* counters = nullptr; // device [2]: iter, trace_row of this group
   long long* mom_window = nullptr;
@@ -57,6 +58,7 @@ struct bnr_handle {
   int n_groups = 0;
   bool graphs_ready = false;
   cudaEvent_t ev_fork = nullptr;
+  ForkJoin fj;                   // side stream for eager sweeps on the whole chain set
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<void*> allocs;
   double* ws = nullptr;          // split-K workspace
@@ -254,6 +256,12 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
     if (ng > d.C) ng = d.C;
     h->n_groups = ng;
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    const bool use_side = getenv("BNR_NO_SIDE") == nullptr;
+    if (use_side) {
+      CK(cudaStreamCreateWithFlags(&h->fj.side, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&h->fj.fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->fj.join, cudaEventDisableTiming));
+    }
     for (int g = 0; g < ng; ++g) {
       ChainGroup& G = h->groups[g];
       // descending priorities break the symmetry between the groups: group 0's grids are dispatched first, so the
@@ -265,6 +273,11 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
       if (getenv("BNR_NO_PRIO")) prio = plo;
       CK(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio));
       CK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
+      if (use_side) {
+        CK(cudaStreamCreateWithPriority(&G.fj.side, cudaStreamNonBlocking, prio));
+        CK(cudaEventCreateWithFlags(&G.fj.fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&G.fj.join, cudaEventDisableTiming));
+      }
       DA(G.ws, x_times_workspace_doubles(d));
       DA(G.counters, 2);
       DA(G.mom_window, 2);
@@ -289,7 +302,13 @@ extern "C" int bnr_destroy(bnr_handle* h) {
   for (int g = 0; g < h->n_groups; ++g) {
     if (h->groups[g].stream) { cudaStreamSynchronize(h->groups[g].stream); cudaStreamDestroy(h->groups[g].stream); }
     if (h->groups[g].done) cudaEventDestroy(h->groups[g].done);
+    if (h->groups[g].fj.side) cudaStreamDestroy(h->groups[g].fj.side);
+    if (h->groups[g].fj.fork) cudaEventDestroy(h->groups[g].fj.fork);
+    if (h->groups[g].fj.join) cudaEventDestroy(h->groups[g].fj.join);
   }
+  if (h->fj.side) cudaStreamDestroy(h->fj.side);
+  if (h->fj.fork) cudaEventDestroy(h->fj.fork);
+  if (h->fj.join) cudaEventDestroy(h->fj.join);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -315,7 +334,7 @@ static void refresh_xg(bnr_handle* h) {
 }
 
 // the gamma conditional: W, v, X v, rhs, G, Cholesky, solves, X' a4, gamma (and optionally S + lambda statistics)
-static void run_gamma(Engine& e, double* ws, cudaStream_t s, int gig_flags) {
+static void run_gamma(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s, int gig_flags) {
   if (e.d.gmode == BNR_GAMMA_QFORM) {
     // P = (X'X + D^-1)/tau2 = L L';  L w = X'(y - mu - X W)/tau2;  L' beta = w + z;  gamma = W + beta
     launch_edge_prep(e, 2, s);                        // W, v = z
@@ -323,7 +342,7 @@ static void run_gamma(Engine& e, double* ws, cudaStream_t s, int gig_flags) {
     launch_rhs(e, s);                                 // (y - mu - X W)/tau2
     launch_x_times(e, 1, e.rhs, e.t, ws, s);          // t = X' rhs
     launch_build_P(e, s);
-    launch_cholesky(e, e.t, s);
+    launch_cholesky(e, e.t, fj, s);
     launch_chol_solve(e, e.t, e.v, s);
     launch_gamma_gig(e, (gig_flags & ~1) | ((gig_flags & 1) ? 4 : 0), s);
     return;
@@ -332,18 +351,18 @@ static void run_gamma(Engine& e, double* ws, cudaStream_t s, int gig_flags) {
   launch_x_times(e, 0, e.v, e.xv, ws, s);
   launch_rhs(e, s);
   launch_syrk_G(e, s);
-  launch_cholesky(e, e.rhs, s);
+  launch_cholesky(e, e.rhs, fj, s);
   launch_chol_solve(e, e.rhs, nullptr, s);
   launch_x_times(e, 1, e.rhs, e.t, ws, s);
   launch_gamma_gig(e, gig_flags, s);
 }
 
 // one full sweep in gibbs_sample! order (src/gibbs.jl:663-677)
-static void enqueue_sweep(Engine& e, double* ws, cudaStream_t s) {
+static void enqueue_sweep(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s) {
   launch_tau2(e, s);
   launch_uxi(e, s);
   std::swap(e.u, e.u_alt);          // u now holds the new draw (pointer swap is baked per captured sweep)
-  run_gamma(e, ws, s, 3);
+  run_gamma(e, ws, fj, s, 3);
   launch_x_times(e, 0, e.gamma, e.xg, ws, s);
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
                        (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
@@ -392,8 +411,8 @@ static int build_graphs(bnr_handle* h) {
     G.e = group_view(h, c0, c1 - c0, G.counters, G.mom_window);
     Engine e = G.e;                  // the capture swaps u / u_alt twice on this copy
     CK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
-    enqueue_sweep(e, G.ws, G.stream);
-    enqueue_sweep(e, G.ws, G.stream);
+    enqueue_sweep(e, G.ws, G.fj, G.stream);
+    enqueue_sweep(e, G.ws, G.fj, G.stream);
     CK(cudaStreamEndCapture(G.stream, &G.graph));
     CK(cudaGraphInstantiate(&G.gexec, G.graph, 0));
   }
@@ -450,7 +469,7 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
   for (; left > 0; --left) {
     drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graphs
     const long long before = g_launches;
-    enqueue_sweep(h->e, h->ws, h->stream);
+    enqueue_sweep(h->e, h->ws, h->fj, h->stream);
     h->launches += g_launches - before;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
@@ -859,7 +878,7 @@ extern "C" int bnr_step(bnr_handle* h, int32_t cond) {
       std::swap(e.u, e.u_alt);
       break;
     case BNR_COND_GAMMA:
-      run_gamma(h->e, h->ws, h->stream, 1);
+      run_gamma(h->e, h->ws, h->fj, h->stream, 1);
       h->xg_valid = false;
       break;
     case BNR_COND_D:
@@ -1073,7 +1092,7 @@ extern "C" int bnr_profile_sweep(bnr_handle* h, float* ms) {
     CK(cudaEventRecord(ev[3], s));
     launch_build_P(e, s);
     CK(cudaEventRecord(ev[4], s));
-    launch_cholesky(e, e.t, s);
+    launch_cholesky(e, e.t, h->fj, s);
     CK(cudaEventRecord(ev[5], s));
     launch_chol_solve(e, e.t, e.v, s);
     CK(cudaEventRecord(ev[6], s));
@@ -1085,7 +1104,7 @@ extern "C" int bnr_profile_sweep(bnr_handle* h, float* ms) {
     CK(cudaEventRecord(ev[3], s));
     launch_syrk_G(e, s);
     CK(cudaEventRecord(ev[4], s));
-    launch_cholesky(e, e.rhs, s);
+    launch_cholesky(e, e.rhs, h->fj, s);
     CK(cudaEventRecord(ev[5], s));
     launch_chol_solve(e, e.rhs, nullptr, s);
     CK(cudaEventRecord(ev[6], s));

@@ -41,8 +41,14 @@ void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, in
 void launch_x_times(const Engine& e, int trans, const double* in, double* out, double* splitk_ws, cudaStream_t s);
 size_t x_times_workspace_doubles(const Dims& d);
 void launch_syrk_G(const Engine& e, cudaStream_t s);         // G_c = X diag(S_c) X' + I (lower tiles)
-// in-place lower Cholesky of every G_c (gdim x gdim) with the forward solve folded in: rhs_c <- L_c^-1 rhs_c
-void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s);
+// optional second stream + events that let launch_cholesky run the off-diagonal panel updates next to the panel
+// factorisation (works eagerly and under stream capture, where it becomes a fork/join of the graph)
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+// in-place lower Cholesky of every G_c (gdim x gdim); the forward solve L w = rhs rides along as a bordering row
+void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStream_t s);
 // rhs_c <- L_c^-T (rhs_c + addz_c); addz may be null
 void launch_chol_solve(const Engine& e, double* rhs, const double* addz, cudaStream_t s);
 void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s);   // X'X, once

@@ -243,7 +243,7 @@ template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
           size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
-          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0) {
+          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0, int part = 0) {
   extern __shared__ __align__(16) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
@@ -269,9 +269,12 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     }
   } else if (MODE == 1) {
     // left-looking update of block column J = origin: tiles (J+1 .. T-1, J) first, the diagonal tile (J, J) last
+    // part 1: the diagonal tile alone, part 2: the tiles below it (the two halves can run concurrently)
     const int T = np / SY_BT, nt = T - origin;
     jb = origin;
-    ib = (blockIdx.y == nt - 1) ? origin : origin + 1 + blockIdx.y;
+    if (part == 1) ib = origin;
+    else if (part == 2) ib = origin + 1 + blockIdx.y;
+    else ib = (blockIdx.y == nt - 1) ? origin : origin + 1 + blockIdx.y;
   } else {
     // MODE 2: panel solve, tiles (J+1 .. T-1, J)
     jb = origin;
@@ -370,8 +373,8 @@ k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ sca
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
-              int nk, int origin) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin, 0.0);
+              int nk, int origin, int part) {
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin, 0.0, nullptr, 0, part);
 }
 
 // panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I > J (in place: a CTA has consumed
@@ -966,8 +969,11 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
   }
 }
 
-// factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix
-void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s) {
+// factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix.
+// Per panel J the critical chain is  diagonal-tile update -> k_potf2_inv -> panel solve; the update of the tiles
+// below the diagonal depends only on the previous panel, so it runs on `side` (a forked branch of the graph) while
+// the latency-bound, one-CTA-per-chain panel factorisation occupies at most C SMs.
+void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
   const int m = d.gmode == 2 ? d.q : d.n;         // first padding row = the bordering row
@@ -975,11 +981,24 @@ void launch_cholesky(const Engine& e, double* rhs, cudaStream_t s) {
   const int T = N / PB;
   ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
   for (int J = 0; J < T; ++J) {
+    const bool fork = fj.side != nullptr && J > 0 && J + 1 < T;
     if (J > 0) {
-      dim3 g2(d.C, T - J);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, J * PB / SY_BK, J);
+      const int nk = J * PB / SY_BK;
+      if (fork) {
+        cudaEventRecord(fj.fork, s);
+        cudaStreamWaitEvent(fj.side, fj.fork, 0);
+        dim3 g2(d.C, T - J - 1);
+        ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, fj.side>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 2);
+        cudaEventRecord(fj.join, fj.side);
+        dim3 g1(d.C, 1);
+        ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 1);
+      } else {
+        dim3 g2(d.C, T - J);
+        ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 0);
+      }
     }
     ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status);
+    if (fork) cudaStreamWaitEvent(s, fj.join, 0);
     if (J + 1 < T) {
       dim3 g1(d.C, T - J - 1);
       ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, e.Linv + (size_t)J * PB * PB,
