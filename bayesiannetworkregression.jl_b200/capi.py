@@ -65,6 +65,7 @@ PROTOTYPES = {
     "bnr_ess": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32, _DP, _DP]),
     "bnr_ess_accumulate": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32]),
     "bnr_ess_device": (C.c_int, [_H, C.POINTER(C.c_void_p), _I64P, C.POINTER(C.c_void_p), _I64P, C.POINTER(C.c_int32)]),
+    "bnr_export_ess": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "bnr_ess_from_stats": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int64, C.c_int32, _DP, _DP]),
     "bnr_gamma_mode": (C.c_int, [_H, C.POINTER(C.c_int32)]),

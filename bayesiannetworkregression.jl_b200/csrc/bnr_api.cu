@@ -1019,6 +1019,16 @@ extern "C" int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov,
   return BNR_OK;
 }
 
+extern "C" int bnr_export_ess(bnr_handle* h, double* dev_acov_dst, double* dev_means_dst) {
+  if (!h || !dev_acov_dst || !dev_means_dst) return fail(BNR_EINVAL, "null argument");
+  if (h->ess_lag < 0) return fail(BNR_ESTATE, "call bnr_ess_accumulate first");
+  const size_t P = (size_t)h->e.d.V + h->e.d.q;
+  CK(cudaMemcpyAsync(dev_acov_dst, h->d_acov, sizeof(double) * (h->ess_lag + 1) * P, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(dev_means_dst, h->d_cmean, sizeof(double) * h->e.d.C * P, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
 extern "C" int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts,
                                   const double* dev_chain_means, int32_t total_chains, int32_t V, int32_t q,
                                   int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma) {

@@ -167,6 +167,9 @@ class Engine:
         check(self._L.bnr_ess_device(self._h, C.byref(pa), C.byref(na), C.byref(pm), C.byref(nm), C.byref(lag)))
         return (pa.value, int(na.value)), (pm.value, int(nm.value)), int(lag.value)
 
+    def export_ess(self, acov_dev_ptr, means_dev_ptr):
+        check(self._L.bnr_export_ess(self._h, C.c_void_p(acov_dev_ptr), C.c_void_p(means_dev_ptr)))
+
     def ess_from_stats(self, acov_ptr, nparts, means_ptr, total_chains, nrows, max_lag):
         ex, eg = np.empty(self.V), np.empty(self.q)
         check(self._L.bnr_ess_from_stats(self.device, C.c_void_p(acov_ptr), int(nparts), C.c_void_p(means_ptr),

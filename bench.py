@@ -113,33 +113,6 @@ def fp64_peak_tflops(torch, dev):
     return best
 
 
-def ess_geyer(x):
-    """Multi-chain ESS (Geyer initial monotone sequence on the pooled autocovariance, no rank normalisation;
-    SURVEY 8(d)).  x: (draws, chains)."""
-    n, m = x.shape
-    if n < 8:
-        return float("nan")
-    xc = x - x.mean(axis=0, keepdims=True)
-    f = np.fft.rfft(xc, n=2 * n, axis=0)
-    acov = np.fft.irfft(f * np.conj(f), axis=0)[:n] / n
-    W = acov[0].mean() * n / (n - 1)
-    B_over_n = x.mean(axis=0).var(ddof=1) if m > 1 else 0.0
-    var_plus = W * (n - 1) / n + B_over_n
-    if not var_plus > 0:
-        return float("nan")
-    rho = 1.0 - (W - acov.mean(axis=1)) / var_plus
-    tau, prev, t = -1.0, np.inf, 0
-    while t + 1 < n:
-        pair = rho[t] + rho[t + 1]
-        if pair < 0:
-            break
-        pair = min(pair, prev)
-        tau += 2.0 * pair
-        prev = pair
-        t += 2
-    return float(n * m / max(tau, 1.0 / math.log10(max(n * m, 10))))
-
-
 def run_reference(args, rank):
     """The reference's algorithm on the host cores (oracle/cpu_baseline.py: dense formulation, one chain per process)."""
     if rank != 0:
@@ -264,12 +237,26 @@ def main():
         rx, rg = eng.rhat()
     status = eng.status()
 
-    # gamma ESS/s on a fixed subset of edges (all chains of this rank, draws of the timed region)
-    sel = np.linspace(0, q - 1, num=min(q, 48)).astype(int)
-    gam = np.stack([eng.get_trace(c, "gamma", Wm + 1, Wm + 1 + K)[:, sel, 0] for c in range(chains)], axis=2)
-    ess = np.array([ess_geyer(gam[:, j, :]) for j in range(len(sel))])
-    ess_med = float(np.nanmedian(ess)) * world
-    ess_min = float(np.nanmin(ess)) * world
+    # gamma ESS/s of EVERY edge coefficient, on the device (bnr_ess_*: per-chain-centred autocovariances by direct
+    # lag sums + Geyer's initial monotone sequence); across GPUs the per-rank autocovariance sums and chain means are
+    # all-gathered over NCCL and reduced identically on every rank
+    max_lag = min(255, K - 1)
+    eng.ess_accumulate(Wm + 1, K, max_lag)
+    (pa, na), (pm, nm), lag = eng.ess_device()
+    if world > 1:
+        a_mine = torch.empty(na, dtype=torch.float64, device=dev)
+        m_mine = torch.empty(nm, dtype=torch.float64, device=dev)
+        eng.export_ess(a_mine.data_ptr(), m_mine.data_ptr())
+        a_all = torch.empty(na * world, dtype=torch.float64, device=dev)
+        m_all = torch.empty(nm * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(a_all, a_mine)
+        dist.all_gather_into_tensor(m_all, m_mine)
+        torch.cuda.synchronize(dev)
+        ess_x, ess_g = eng.ess_from_stats(a_all.data_ptr(), world, m_all.data_ptr(), chains * world, K, lag)
+    else:
+        ess_x, ess_g = eng.ess_from_stats(pa, 1, pm, chains, K, lag)
+    ess_med = float(np.nanmedian(ess_g))
+    ess_min = float(np.nanmin(ess_g))
 
     # ---------------- per-phase CUDA-event profile of eager sweeps (roofline numerator) ----------------
     phases = {}
@@ -277,9 +264,18 @@ def main():
         for k, v in eng.profile_sweep().items():
             phases.setdefault(k, []).append(v)
     phases = {k: float(np.mean(v)) for k, v in phases.items()}
-    syrk_ms = phases["syrk"]
-    syrk_flops = chains * float(n) * n * q            # n^2 q per chain-iteration (lower half, mul+add)
-    achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
+    gmode = eng.gamma_mode
+    if gmode == "nform":
+        # dominant kernel: G = X D X' + I.  SURVEY 8(d): n^2 q flops per chain-iteration (lower half, mul+add)
+        dom_kernel = "k_gram_syrk (X diag(S) X' + I, DMMA m8n8k4, TMA ring)"
+        dom_ms = phases["syrk"]
+        dom_flops = chains * float(n) * n * q
+    else:
+        # q-form: the batched blocked Cholesky of the q x q precision dominates; q^3/3 flops per chain-iteration
+        dom_kernel = "blocked Cholesky of P = (X'X + D^-1)/tau2 (k_chol_update + k_potf2_inv + k_trsm_dmma)"
+        dom_ms = phases["cholesky"]
+        dom_flops = chains * float(q) ** 3 / 3.0
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     if os.path.exists(tpath):
@@ -329,15 +325,17 @@ def main():
                     "d2h_bytes_per_step": d2h, "includes": "cudaMalloc + H2D of X,y + prior init + K sweeps + D2H of "
                     "chain-1 gamma/xi traces and R-hat"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "k_syrk<0> (X diag(S) X' + I, DMMA m8n8k4)",
+            "roofline": {"bound": "tensor", "kernel": dom_kernel,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "ms_per_launch": syrk_ms, "flops_per_launch": syrk_flops,
+                         "traffic": traffic, "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
                          "peak_source": "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
             "cpu_baseline": cpu,
-            "gamma_ess_per_sec": {"median": ess_med / (max_over_ranks(dev_ms) * 1e-3) if world == 1 else None,
-                                  "min": ess_min / (max_over_ranks(dev_ms) * 1e-3) if world == 1 else None,
-                                  "edges": int(len(sel)), "draws_per_chain": K,
-                                  "note": "Geyer multi-chain ESS over the timed draws (short window, indicative)"},
+            "gamma_ess_per_sec": {"median": ess_med / (max_over_ranks(dev_ms) * 1e-3),
+                                  "min": ess_min / (max_over_ranks(dev_ms) * 1e-3),
+                                  "edges": int(q), "draws_per_chain": K, "chains": chains * world, "max_lag": lag,
+                                  "note": "device-side multi-chain Geyer ESS of every gamma_j over the timed draws "
+                                          "(short window right after warm-up: indicative, not a converged-run figure)"},
+            "gamma_mode": gmode,
             "algorithmic_tflops": value * algo_flops / 1e12,
             "phases_ms": phases,
             "wall_ms_per_step": wall_ms / K,

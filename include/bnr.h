@@ -203,6 +203,8 @@ int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag, do
 int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag);
 int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov, double** chain_mean, int64_t* n_mean,
                    int32_t* max_lag);
+/* copy the two statistics buffers into caller-owned DEVICE memory (the inputs of the NCCL all-gathers) */
+int bnr_export_ess(bnr_handle* h, double* dev_acov_dst, double* dev_means_dst);
 int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts, const double* dev_chain_means,
                        int32_t total_chains, int32_t V, int32_t q, int64_t nrows, int32_t max_lag, double* ess_xi,
                        double* ess_gamma);

@@ -537,6 +537,38 @@ def ess_geyer(x, max_lag=None):
     return float(nm / max(tau, 1.0 / math.log10(max(nm, 10))))
 
 
+def ess_stats(x, max_lag):
+    """Per-rank sufficient statistics of ess_geyer for x (draws, chains): sum over the chains of the biased
+    per-chain-centred autocovariances, lags 0..max_lag, and the chain means -- the two buffers of bnr_ess_device."""
+    n = x.shape[0]
+    xc = x - x.mean(axis=0, keepdims=True)
+    acov = np.stack([(xc[: n - t] * xc[t:]).sum(axis=0) / n for t in range(max_lag + 1)])
+    return acov.sum(axis=1), x.mean(axis=0)
+
+
+def ess_from_stats(acov_parts, chain_means, n, max_lag):
+    """ess_geyer from gathered statistics (bnr_ess_from_stats): acov_parts (ranks, max_lag+1), chain_means (chains,)."""
+    m = len(chain_means)
+    acov = np.asarray(acov_parts).sum(axis=0) / m
+    W = acov[0] * n / (n - 1)
+    B_over_n = np.var(chain_means, ddof=1) if m > 1 else 0.0
+    var_plus = W * (n - 1) / n + B_over_n
+    if not var_plus > 0:
+        return float("nan")
+    rho = 1.0 - (W - acov) / var_plus
+    tau, prev, t = -1.0, np.inf, 0
+    while t + 1 <= max_lag and t + 1 < n:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        pair = min(pair, prev)
+        tau += 2.0 * pair
+        prev = pair
+        t += 2
+    nm = n * m
+    return float(nm / max(tau, 1.0 / math.log10(max(nm, 10))))
+
+
 def julia_round(x):
     """Julia round(): ties to even."""
     return int(np.rint(x))

@@ -39,7 +39,20 @@ def _worker(rank, world, port, traces, q):
     h = traces.shape[0] // 2
     mean = mom[:, :, :, 0].reshape(-1, traces.shape[1])
     m2 = mom[:, :, :, 1].reshape(-1, traces.shape[1])
-    q.put((rank, O.rhat_from_moments(mean, m2, h)))
+    # ESS statistics: per-rank autocovariance sums [L+1][param] and chain means [chain][param], gathered the same way
+    L = 15
+    loc = traces[:, :, rank * per:(rank + 1) * per]
+    st = [O.ess_stats(loc[:, p, :], L) for p in range(traces.shape[1])]
+    a_mine = torch.from_numpy(np.stack([s_[0] for s_ in st], axis=1).ravel().copy())           # [L+1][param]
+    m_mine = torch.from_numpy(np.stack([s_[1] for s_ in st], axis=1).ravel().copy())           # [chain][param]
+    a_all = torch.empty(a_mine.numel() * world, dtype=torch.float64)
+    m_all = torch.empty(m_mine.numel() * world, dtype=torch.float64)
+    dist.all_gather_into_tensor(a_all, a_mine)
+    dist.all_gather_into_tensor(m_all, m_mine)
+    A = a_all.numpy().reshape(world, L + 1, traces.shape[1])
+    M = m_all.numpy().reshape(world * per, traces.shape[1])
+    ess = np.array([O.ess_from_stats(A[:, :, p], M[:, p], traces.shape[0], L) for p in range(traces.shape[1])])
+    q.put((rank, (O.rhat_from_moments(mean, m2, h), ess)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,6 +75,9 @@ def test_two_rank_moment_gather_gives_global_rhat():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    want_ess = np.array([O.ess_geyer(traces[:, p, :], 15) for p in range(params)])
     for r in range(2):
-        np.testing.assert_allclose(got[r], want, rtol=1e-11)
-    np.testing.assert_array_equal(got[0], got[1])      # every rank gets the identical reduction
+        np.testing.assert_allclose(got[r][0], want, rtol=1e-11)
+        np.testing.assert_allclose(got[r][1], want_ess, rtol=1e-10)
+    np.testing.assert_array_equal(got[0][0], got[1][0])      # every rank gets the identical reduction
+    np.testing.assert_array_equal(got[0][1], got[1][1])
