@@ -11,7 +11,8 @@ __graft_entry__.load_package) and registered as module `bnr_b200`.
 """
 from .capi import lib, BnrError, check, Params, VAR, COND, AUX, STATUS_BITS  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .io import read_matrix_networks, read_adjacency_csvs, read_responses  # noqa: F401
 from .fit import Fit, Summary, Results, BNRSummary, Table, setup_X, lower_triangle, create_lower_tri  # noqa: F401
 
 __all__ = ["Fit", "Summary", "Results", "BNRSummary", "Table", "Engine", "BnrError", "setup_X",
-           "lower_triangle", "create_lower_tri", "lib"]
+           "lower_triangle", "create_lower_tri", "lib", "read_matrix_networks", "read_adjacency_csvs", "read_responses"]

@@ -59,6 +59,21 @@ def main():
     t1 = np.loadtxt(os.path.join(REF, "test/data/test1.csv"), delimiter=",", skiprows=1)
     out["test1.X"] = t1[:, :190].copy()
     out["test1.y"] = t1[:, 190].copy()
+    # BASELINE config 1 input: the shipped vectorised example (100 x 465 lower triangles + response in the last
+    # column, docs/src/man/inputdata.md:83-91) and the posterior tables of the reference's own stored 50 000-iteration
+    # fit of the same data (older diagonal-free model, R = 7): soft level-2 references
+    ex = np.loadtxt(os.path.join(REF, "examples/matrix_networks.csv"), delimiter=",", skiprows=1)
+    out["example.X"] = ex[:, :465].copy()
+    out["example.y"] = ex[:, 465].copy()
+    tdir = os.path.join(REF, "test/data")
+    pre = "R=7_mu=1.6_n_microbes=22_nu=10_out="
+    suf = "_pi=0.8_samplesize=100_simnum=1.csv"
+    ed = np.genfromtxt(os.path.join(tdir, pre + "edges" + suf), delimiter=",", names=True)
+    nd = np.genfromtxt(os.path.join(tdir, pre + "nodes" + suf), delimiter=",", names=True)
+    out["example.ref_edge_mean"] = np.asarray(ed["mean"], dtype=np.float64)
+    out["example.ref_edge_lo"] = np.asarray(ed["0025"], dtype=np.float64)
+    out["example.ref_edge_hi"] = np.asarray(ed["0975"], dtype=np.float64)
+    out["example.ref_xi_posterior"] = np.asarray(nd["Xi_posterior"], dtype=np.float64)
     out["example.true_xi"] = _csv_col(os.path.join(REF, "examples/true_xi.csv"))
     out["example.true_b"] = _csv_col(os.path.join(REF, "examples/true_b.csv"))
     dst = os.path.join(os.path.dirname(__file__), "golden.npz")

@@ -157,3 +157,30 @@ def test_table_aliases(bnr):
     assert t["γ"] is t["gamma"] is t.gamma is t.γ
     assert t["ξ"] is t.xi and t["τ²"] is t.tau2 and t["πᵥ"] is t.pi
     assert len(t) == 3
+
+
+def test_input_formats_roundtrip(bnr, tmp_path, golden):
+    """The documented input workflows (docs/src/man/inputdata.md): vectorised CSV with the response in the last
+    column, and one CSV per adjacency matrix + responses.csv; both must give the same n x q design matrix."""
+    X, y = golden["example.X"][:7], golden["example.y"][:7]
+    V = 30
+    vec = tmp_path / "matrix_networks.csv"
+    hdr = ",".join("x%d" % (i + 1) for i in range(X.shape[1] + 1))
+    np.savetxt(vec, np.column_stack([X, y]), delimiter=",", header=hdr, comments="")
+    Xr, yr = bnr.read_matrix_networks(str(vec))
+    np.testing.assert_allclose(Xr, X, rtol=1e-15)
+    np.testing.assert_allclose(yr, y, rtol=1e-15)
+    for i in range(len(y)):
+        A = bnr.create_lower_tri(X[i], V)
+        A = A + np.tril(A, -1).T
+        np.savetxt(tmp_path / ("data%d.csv" % (i + 1)), A, delimiter=",",
+                   header=",".join("Column%d" % (c + 1) for c in range(V)), comments="")
+    np.savetxt(tmp_path / "responses.csv", y, header="Column1", comments="")
+    mats = bnr.read_adjacency_csvs(str(tmp_path), len(y))
+    assert len(mats) == len(y) and mats[0].shape == (V, V)
+    np.testing.assert_allclose(bnr.setup_X(mats, True), X, rtol=1e-15)
+    np.testing.assert_allclose(bnr.read_responses(str(tmp_path / "responses.csv")), y, rtol=1e-15)
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.csv"
+        np.savetxt(bad, np.zeros((3, 8)), delimiter=",", header="a,b,c,d,e,f,g,h", comments="")
+        bnr.read_matrix_networks(str(bad))

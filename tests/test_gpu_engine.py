@@ -407,3 +407,35 @@ def test_full_size_runs_are_bitwise_reproducible_across_chain_groups(bnr, shape)
             for c in range(C):
                 for k in ref[c]:
                     np.testing.assert_array_equal(np.asarray(st[c][k]), np.asarray(ref[c][k]), err_msg="%s chain %d groups %d" % (k, c, groups))
+
+
+def test_config1_shipped_example(bnr, golden):
+    """BASELINE config 1: Fit! on the shipped example (examples/matrix_networks.csv: n=100, V=30, q=465), R=5.
+    The reference's own stored 50 000-iteration fit of this data (older diagonal-free model, R=7;
+    test/data/R=7_mu=1.6_n_microbes=22_*.csv) and the simulation truth (examples/true_xi.csv, true_b.csv) are
+    soft level-2 references: the influential-node calls must match, posterior edge means must track the stored
+    ones, and the stored 95% intervals must cover our posterior means for nearly all edges."""
+    X, y = golden["example.X"], golden["example.y"]
+    res = bnr.Fit(X, y, 5, nburn=12000, nsamples=8000, num_chains=8, seed=2358, x_transform=False, filename=None,
+                  psrf_cutoff=1e9, return_state="none")
+    assert res.extra["gamma_mode"] == "nform" and not (res.extra["status"] & ~1).any()
+    out = bnr.Summary(res)
+    prob = out.prob_nodes["probability"]
+    true_xi = golden["example.true_xi"]
+    ref_prob = golden["example.ref_xi_posterior"]
+    assert ((prob > 0.5) == (true_xi > 0.5)).mean() >= 0.9, prob
+    assert ((prob > 0.5) == (ref_prob > 0.5)).mean() >= 0.9, prob
+    # edges: our table has the diagonal (465 rows), the stored one does not (435 rows, same column-major order)
+    offdiag = out.edge_coef["node1"] != out.edge_coef["node2"]
+    est = out.edge_coef["estimate"][offdiag]
+    ref_mean, lo, hi = golden["example.ref_edge_mean"], golden["example.ref_edge_lo"], golden["example.ref_edge_hi"]
+    assert np.corrcoef(est, ref_mean)[0, 1] > 0.9
+    assert np.corrcoef(est, golden["example.true_b"])[0, 1] > 0.6
+    assert np.mean((est >= lo - 0.25) & (est <= hi + 0.25)) > 0.95
+    # (the diagonal columns of X are all zero: those coefficients are draws from N(W_kk, tau2 S), W_kk = u_k' Lambda u_k,
+    #  so they carry no data information and are left out of the comparison)
+    sig = (out.edge_coef["lower_bound"] > 0) | (out.edge_coef["upper_bound"] < 0)
+    # significant-edge calls: edges between truly influential nodes dominate the calls
+    tb = golden["example.true_b"] != 0
+    called = sig[offdiag]
+    assert called.sum() > 20 and (called & tb).sum() / max(called.sum(), 1) > 0.8
