@@ -210,6 +210,16 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
   DA(e.G, C * d.gdim * d.gdim + 2048);
   DA(e.Linv, C * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N);
+  e.syrk_ws = nullptr; e.syrk_ws_cap = 0;
+  if (d.gmode == BNR_GAMMA_NFORM) {
+    // few chains x tiles: the SYRK splits its contraction (see launch_syrk_G).  The split count is fixed per handle
+    // from its total chain count, so the chain grouping never changes the summation order.
+    const int smax = syrk_splits(d, d.C);
+    if (smax > 1) {
+      e.syrk_ws_cap = smax - 1;
+      DA(e.syrk_ws, C * (size_t)e.syrk_ws_cap * d.gdim * d.gdim);
+    }
+  }
   e.XtX = nullptr;
   if (d.gmode == BNR_GAMMA_QFORM) {
     // X'X once: row-major copy of X as the SYRK operand (k-major over the n samples), unit scales, no identity
@@ -383,7 +393,7 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   v.gamma += c * d.qp; v.S += c * d.qp; v.W += c * d.qp; v.v += c * d.qp; v.t += c * d.qp;
   v.M += c * d.R * d.R; v.lambda += c * d.R; v.pi += c * 3 * d.R;
   v.xg += c * d.np; v.xv += c * d.np; v.rhs += c * d.np;
-  v.G += c * d.gdim * d.gdim; v.Linv += c * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N;
+  v.G += c * d.gdim * d.gdim; if (v.syrk_ws) v.syrk_ws += c * (size_t)v.syrk_ws_cap * d.gdim * d.gdim; v.Linv += c * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N;
   v.partials += c * d.nparts * (2 * MAX_R + 1);
   v.moments += c * 2 * (d.V + d.q) * 2;
   if (v.tr_gx) v.tr_gx += c * v.trace_rows * (d.V + d.q);

@@ -103,6 +103,8 @@ struct Engine {
   double* xv;       // [C][np]  X (W + delta1)
   double* rhs;      // [C][np]  a1 - a3, then L^-1 rhs, then a4 (in place); q-form: (y - mu - X W)/tau2
   double* G;        // [C][gdim*gdim] col-major, lower triangle used
+  double* syrk_ws;  // [C][syrk_ws_cap][gdim*gdim] partial Gram matrices of the k-split SYRK (nullptr: never split)
+  int syrk_ws_cap;  // splits - 1, fixed per handle
   double* Linv;     // [C][gdim/128][128*128]  inverses of the 128 x 128 diagonal blocks of the factor (column-major)
   double* partials; // [C][nparts][2*MAX_R+1]  block partial sums: A_r, B_r (lambda), sum S
   int* status;      // [C]

@@ -41,6 +41,7 @@ void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, in
 void launch_x_times(const Engine& e, int trans, const double* in, double* out, double* splitk_ws, cudaStream_t s);
 size_t x_times_workspace_doubles(const Dims& d);
 void launch_syrk_G(const Engine& e, cudaStream_t s);         // G_c = X diag(S_c) X' + I (lower tiles)
+int syrk_splits(const Dims& d, int C);                        // k-splits launch_syrk_G uses for a batch of C chains
 // optional second stream + events that let launch_cholesky run the off-diagonal panel updates next to the panel
 // factorisation (works eagerly and under stream capture, where it becomes a fork/join of the graph)
 struct ForkJoin {

@@ -79,6 +79,7 @@ constexpr int SY_BT = 128;        // tile edge
 constexpr int SY_BK = 16;         // k-step
 constexpr int SY_LDS = 132;       // smem row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
 constexpr int SY_STAGES = 4;
+constexpr int SYRK_MAX_SPLITS = 8;
 constexpr int SY_STAGE_DBL = 2 * SY_BK * SY_LDS + SY_BK;   // two operand tiles + 16 scales
 constexpr int SY_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgroup (one active lane)
 constexpr int SY_PRODUCER_REGS = 40, SY_CONSUMER_REGS = 232;   // 128*40 + 256*232 = 64512 = 384*168
@@ -365,10 +366,41 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   }
 }
 
+// gridDim.z > 1 splits the contraction: split z handles k-steps [z * nk_split, ...) and writes its partial tile to
+// ws[c][z - 1] (split 0 writes G itself, identity included); k_syrk_splitk_reduce adds them in a fixed order.  Used
+// when chains x tiles cannot fill the SMs (few chains, large q: BASELINE config 4).
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ scale, size_t scale_stride,
-            double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk, double diag_add) {
-  syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk, 0, diag_add);
+            double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk, double diag_add,
+            int nk_split, double* __restrict__ ws, int ws_cap) {
+  const int z = blockIdx.z;
+  if (z == 0) {
+    syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk < nk_split ? nk : nk_split, 0, diag_add);
+  } else {
+    const int kt0 = z * nk_split;
+    const int nkl = (nk - kt0) < nk_split ? (nk - kt0) : nk_split;
+    syrk_body<0>(X + (size_t)kt0 * SY_BK * ld, 0, ld, scale + (size_t)kt0 * SY_BK, scale_stride,
+                 ws + (size_t)(z - 1) * g_chain_stride, (size_t)ws_cap * g_chain_stride, np, nvalid, nkl, 0, 0.0);
+  }
+}
+
+// G_c (lower tiles) += sum_z ws[c][z].  grid = (lower tiles, C), block = 256
+__global__ void __launch_bounds__(256) k_syrk_splitk_reduce(double* __restrict__ G, size_t g_chain_stride, int np,
+                                                            const double* __restrict__ ws, int ws_cap, int nz) {
+  const int T = np / SY_BT, c = blockIdx.y;
+  int t = blockIdx.x, ib = 0;
+  while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+  const int jb = t - ib * (ib + 1) / 2;
+  (void)T;
+  double* Gc = G + (size_t)c * g_chain_stride;
+  const double* wc = ws + (size_t)c * ws_cap * g_chain_stride;
+  for (int id = threadIdx.x; id < SY_BT * SY_BT; id += 256) {
+    const int i = ib * SY_BT + (id & (SY_BT - 1)), j = jb * SY_BT + (id >> 7);
+    const size_t o = (size_t)j * np + i;
+    double v = Gc[o];
+    for (int z = 0; z < nz; ++z) v += wc[(size_t)z * g_chain_stride + o];
+    Gc[o] = v;
+  }
 }
 
 __global__ void __launch_bounds__(SY_THREADS, 1)
@@ -906,21 +938,39 @@ void linalg_setup() {
   cudaFuncSetAttribute(k_bwd_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
+// k-splits of the SYRK for a batch of C chains: enough CTAs for ~2 per SM, at least 32 k-steps per split
+int syrk_splits(const Dims& d, int C) {
+  const int T = d.np / SY_BT, tiles = T * (T + 1) / 2, nk = d.qp / SY_BK;
+  if (tiles * C >= 148) return 1;
+  int s = (2 * 148 + tiles * C - 1) / (tiles * C);
+  if (s > nk / 32) s = nk / 32;
+  if (s > SYRK_MAX_SPLITS) s = SYRK_MAX_SPLITS;
+  return s < 1 ? 1 : s;
+}
+
 void launch_syrk_G(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;
   const int T = d.np / SY_BT;
+  const int nk = d.qp / SY_BK;
+  const int ns = e.syrk_ws ? e.syrk_ws_cap + 1 : 1;   // fixed per handle: chain groups must not change the summation order
+  const int nk_split = (nk + ns - 1) / ns;
 #if defined(SYRK_LAB_ONLY_DIAG)
-  dim3 grid(d.C, T);
+  dim3 grid(d.C, T, ns);
 #elif defined(SYRK_LAB_ONLY_OFFDIAG)
-  dim3 grid(d.C, T * (T - 1) / 2);
+  dim3 grid(d.C, T * (T - 1) / 2, ns);
 #else
-  dim3 grid(d.C, T * (T + 1) / 2);
+  dim3 grid(d.C, T * (T + 1) / 2, ns);
 #endif
-  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, (size_t)d.np * d.np, d.np, d.n,
-                                                            d.qp / SY_BK, 1.0);
+  const size_t gs = (size_t)d.np * d.np;
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, gs, d.np, d.n, nk, 1.0,
+                                                            nk_split, e.syrk_ws, e.syrk_ws_cap);
+  if (ns > 1) {
+    dim3 g2(T * (T + 1) / 2, d.C);
+    ++g_launches; k_syrk_splitk_reduce<<<g2, 256, 0, s>>>(e.G, gs, d.np, e.syrk_ws, e.syrk_ws_cap, ns - 1);
+  }
   if (e.aux.G_copy) {
     dim3 g2(d.np, d.C);
-    ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, (size_t)d.np * d.np, d.np, e.aux.G_copy);
+    ++g_launches; k_copy_sym<<<g2, 256, 0, s>>>(e.G, gs, d.np, e.aux.G_copy);
   }
 }
 
@@ -932,7 +982,8 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
 void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s) {
   const int T = d.qp / SY_BT;
   dim3 grid(1, T * (T + 1) / 2);
-  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(XT, d.qp, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0);
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(XT, d.qp, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0,
+                                                            d.np / SY_BK, nullptr, 0);
 }
 
 // P_c lower triangle from XtX, S_c, tau2_c; padding rows/columns get the identity so the factorisation stays PD.

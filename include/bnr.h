@@ -30,7 +30,9 @@
  *    Array{Float64,3}(rows, d1, d2) can wrap the buffer directly.
  *  - all arithmetic is FP64.  Random numbers: Philox4x32-10, key = (seed, global chain id),
  *    counter = (sub-block, element, draw site, iteration): results do not depend on how chains are
- *    distributed over handles/GPUs.
+ *    distributed over handles/GPUs or chain groups (bit for bit, with one exception: when a handle
+ *    holds so few chains that the Gram SYRK splits its contraction -- num_chains x tiles < 148 and
+ *    q >= 1024 -- the split count, hence the rounding of G, depends on the handle's chain count).
  *  - a handle is not thread-safe.
  */
 #ifndef BNR_H

@@ -439,3 +439,30 @@ def test_config1_shipped_example(bnr, golden):
     tb = golden["example.true_b"] != 0
     called = sig[offdiag]
     assert called.sum() > 20 and (called & tb).sum() / max(called.sum(), 1) > 0.8
+
+
+def test_syrk_split_k_path(bnr):
+    """Few chains x large q (BASELINE config 4's regime): the Gram SYRK splits its contraction over gridDim.z and adds
+    the partial matrices in a fixed order.  G must still equal X D X' + I to rounding and the run stay reproducible."""
+    V, R, n, C = 64, 3, 200, 2          # q = 2080 -> 130 k-steps -> 4 splits for 2 x 3 tiles
+    rng = np.random.default_rng(3)
+    q = V * (V + 1) // 2
+    X = rng.normal(size=(n, q))
+    y = X[:, :10].sum(axis=1) + rng.normal(size=n)
+    outs = []
+    for rep in range(2):
+        with bnr.Engine(X, y, R, num_chains=C, seed=5, chain_groups=1) as eng:
+            assert eng.gamma_mode == "nform"
+            eng.init_state()
+            eng.run(2)
+            eng.enable_aux(True)
+            S_old = eng.get_state(1, "S")[:, 0].copy()
+            eng.step("tau2"); eng.step("u_xi"); eng.step("gamma")
+            G = eng.get_aux(1, "G").reshape(n, n).T
+            want = (X * S_old[None, :]) @ X.T + np.eye(n)
+            assert np.abs(G - want).max() <= 1e-12 * np.abs(want).max()
+            L = eng.get_aux(1, "G_chol").reshape(n, n).T
+            assert np.abs(L @ L.T - want).max() <= 1e-11 * np.abs(want).max()
+            outs.append(eng.get_state(1, "gamma").copy())
+            assert not (eng.status() & ~1).any()
+    np.testing.assert_array_equal(outs[0], outs[1])
