@@ -432,7 +432,7 @@ k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int
 //                     is factored in shared memory (32-wide steps: one warp factors 32 x 32 in registers with
 //                     shuffles, a thread per row eliminates below, everybody updates the trailing part in 2 x 2
 //                     register tiles), goes back with bulk stores, and is then INVERTED in place (32 x 32 diagonal
-//                     inverses by substitution, off-diagonal blocks by small products) -> Linv[c][J]
+//                     inverses by substitution, off-diagonal blocks by the recursive 2 x 2 block formula) -> Linv[c][J]
 //       k_trsm_dmma   (DMMA): G[I, J] <- G[I, J] Linv_J' for I > J -- the panel solve is a GEMM
 //   * backward solve L' x = w (+ z): k_bwd_stream, one CTA per chain streams the factor once (bulk copies into a
 //     shared-memory ring, 64-column half blocks), every step is a block mat-vec; the diagonal blocks use Linv.
@@ -440,7 +440,7 @@ k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int
 constexpr int PB = 128;            // panel / diagonal block size
 constexpr int XD_LD = 34;          // column stride of the 32 x 32 scratch blocks (even: 16-byte loads; 34: spreads banks)
 constexpr int XD_BLK = 32 * XD_LD;
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PB + 7 * XD_BLK + PB) + 16;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PB + 9 * XD_BLK + PB + 64) + 16;
 constexpr int CHOL_MAX_DIM = 4096; // largest factored dimension (shared-memory solution vector of the back solve)
 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
@@ -505,9 +505,11 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   extern __shared__ __align__(16) double sm[];
   double* A = sm;                          // column-major 128 x 128 working block: A[col * PB + row]
   double* Xd = sm + PB * PB;               // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
-  double* Tm = Xd + 4 * XD_BLK;            // [3] products of the off-diagonal stage
-  double* dall = Tm + 3 * XD_BLK;          // [128] reciprocal diagonal of L
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(dall + PB);
+  double* Tm = Xd + 4 * XD_BLK;            // [4] intermediate products of the inverse
+  double* X10s = Tm + 4 * XD_BLK;          // [1] copy of the (1,0) inverse block with the conflict-free stride
+  double* dall = X10s + XD_BLK;            // [128] reciprocal diagonal of L
+  double* Lcol = dall + PB;                // [2][32] current column of the 32 x 32 factorisation (double-buffered)
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* D = G + (size_t)c * chain_stride + (size_t)J * PB * N + (size_t)J * PB;
   if (tid == 0) {
@@ -525,23 +527,29 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
     const int o = s * 32;
     if (warp == 0) {
       // 32 x 32 Cholesky in registers: lane r holds row o+r (columns o .. o+31); entries above the diagonal are
-      // whatever the block held there and never reach a valid entry
+      // whatever the block held there and never reach a valid entry.  Column j is broadcast through shared memory
+      // (one store + broadcast loads instead of 31 shuffles), and the next pivot is updated and fetched FIRST so
+      // its rsqrt chain runs under the remaining updates of column j.
       double a[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] = A[(o + j) * PB + o + lane];
+      double djj = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const double djj = __shfl_sync(0xffffffffu, a[j], j);
         if (!(djj > 0.0)) bad = true;
         const double inv = rsqrt(djj);
         const double lj = (lane == j) ? djj * inv : a[j] * inv;
         a[j] = lj;
+        double* lc = Lcol + (j & 1) * 32;
+        lc[lane] = lj;
         if (lane == j) dall[o + j] = inv;
-#pragma unroll
-        for (int cc = j + 1; cc < 32; ++cc) {
-          const double lcj = __shfl_sync(0xffffffffu, lj, cc);
-          a[cc] -= lj * lcj;
+        __syncwarp();
+        if (j + 1 < 32) {
+          a[j + 1] -= lj * lc[j + 1];
+          djj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
         }
+#pragma unroll
+        for (int cc = j + 2; cc < 32; ++cc) a[cc] -= lj * lc[cc];
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -618,32 +626,65 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
     for (int i = 0; i < 32; ++i) Xd[b * XD_BLK + j * XD_LD + i] = (i >= j) ? x[i] : 0.0;
   }
   __syncthreads();   // also orders the bulk-store reads (tid 0 waited above) before the in-place overwrite below
-  // (2) block columns from the right: X_ij = -(sum_{k=j+1..i} X_ik L_kj) X_jj for i = j+1 .. 3; X_ik (k > j) is
-  //     final, L_kj (column j) is still the factor because column j is overwritten only at the end of its step
-  for (int j = 2; j >= 0; --j) {
-    const int nb = 3 - j;
-    for (int t = tid; t < nb * 128; t += 256) {
-      const int bi = t >> 7, i = j + 1 + bi, tt = t & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
-      double acc[4][2] = {};
-      for (int k = j + 1; k <= i; ++k) {
-        const double* Lkj = A + (32 * j) * PB + 32 * k;
-        if (k == i) blk32_fma(acc, Xd + i * XD_BLK, XD_LD, Lkj, PB, r4, c2);
-        else blk32_fma(acc, A + (32 * k) * PB + 32 * i, PB, Lkj, PB, r4, c2);
-      }
+  // (2) off-diagonal 32 x 32 blocks of the inverse by the recursive 2 x 2 block formula
+  //        [[A, 0], [C, B]]^-1 = [[A^-1, 0], [-B^-1 C A^-1, B^-1]],
+  //     first inside the two 64 x 64 diagonal blocks, then for the 64 x 64 block below them.  Every stage is a set of
+  //     32 x 32 x 32 products with the same cost per thread (4 x 2 register tiles, one or two tasks per thread).
+  //     Operands that are read column-wise (the right factors) sit in the stride-34 scratch blocks.
+  auto blkA = [&](int i, int j) { return A + (32 * j) * PB + 32 * i; };        // block (i, j) of the working matrix
+  {
+    // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1      stage 2: X_(2b+1, 2b) = -Xd_(2b+1) T_b
+    const int b = tid >> 7, tt = tid & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
+    double acc[4][2] = {};
+    blk32_fma(acc, blkA(2 * b + 1, 2 * b), PB, Xd + (2 * b) * XD_BLK, XD_LD, r4, c2);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        Tm[bi * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
-        Tm[bi * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
-      }
+    for (int a = 0; a < 4; ++a) {
+      Tm[b * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
+      Tm[b * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
     }
     __syncthreads();
-    for (int t = tid; t < nb * 128; t += 256) {
-      const int bi = t >> 7, i = j + 1 + bi, tt = t & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
-      double acc[4][2] = {};
-      blk32_fma(acc, Tm + bi * XD_BLK, XD_LD, Xd + j * XD_BLK, XD_LD, r4, c2);
-      double* dst = A + (32 * j + c2) * PB + 32 * i + r4;
+    double acc2[4][2] = {};
+    blk32_fma(acc2, Xd + (2 * b + 1) * XD_BLK, XD_LD, Tm + b * XD_BLK, XD_LD, r4, c2);
+    double* dst = blkA(2 * b + 1, 2 * b) + c2 * PB + r4;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) { dst[a] = -acc[a][0]; dst[PB + a] = -acc[a][1]; }
+    for (int a = 0; a < 4; ++a) {
+      dst[a] = -acc2[a][0];
+      dst[PB + a] = -acc2[a][1];
+      if (b == 0) { X10s[c2 * XD_LD + r4 + a] = -acc2[a][0]; X10s[(c2 + 1) * XD_LD + r4 + a] = -acc2[a][1]; }
+    }
+    __syncthreads();
+  }
+  {
+    // stage 3: T2 = C A^-1 with C = blocks (2..3, 0..1):  T2_(i,0) = C_(i,0) X_00 + C_(i,1) X_10,  T2_(i,1) = C_(i,1) X_11.
+    // every thread takes one tile of a column-0 block (two products) and one of a column-1 block (one product)
+    const int ib = tid >> 7, tt = tid & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2, i = 2 + ib;
+    double acc[4][2] = {};
+    blk32_fma(acc, blkA(i, 0), PB, Xd, XD_LD, r4, c2);
+    blk32_fma(acc, blkA(i, 1), PB, X10s, XD_LD, r4, c2);
+    double acc1[4][2] = {};
+    blk32_fma(acc1, blkA(i, 1), PB, Xd + XD_BLK, XD_LD, r4, c2);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      Tm[(2 * ib) * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
+      Tm[(2 * ib) * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
+      Tm[(2 * ib + 1) * XD_BLK + c2 * XD_LD + r4 + a] = acc1[a][0];
+      Tm[(2 * ib + 1) * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc1[a][1];
+    }
+    __syncthreads();
+    // stage 4: X_C = -B^-1 T2:  X_(2,j) = -X_22 T2_(2,j),  X_(3,j) = -(X_32 T2_(2,j) + X_33 T2_(3,j)), j = 0, 1.
+    // thread -> column block j = tid >> 7: one tile of row block 2 (one product) and one of row block 3 (two products)
+    const int jb = tid >> 7;
+    double s2[4][2] = {};
+    blk32_fma(s2, Xd + 2 * XD_BLK, XD_LD, Tm + jb * XD_BLK, XD_LD, r4, c2);                 // T2_(2,jb) is Tm[jb]
+    double s3[4][2] = {};
+    blk32_fma(s3, blkA(3, 2), PB, Tm + jb * XD_BLK, XD_LD, r4, c2);
+    blk32_fma(s3, Xd + 3 * XD_BLK, XD_LD, Tm + (2 + jb) * XD_BLK, XD_LD, r4, c2);           // T2_(3,jb) is Tm[2 + jb]
+    double* d2 = blkA(2, jb) + c2 * PB + r4;
+    double* d3 = blkA(3, jb) + c2 * PB + r4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      d2[a] = -s2[a][0]; d2[PB + a] = -s2[a][1];
+      d3[a] = -s3[a][0]; d3[PB + a] = -s3[a][1];
     }
     __syncthreads();
   }
