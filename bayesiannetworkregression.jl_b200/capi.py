@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbnr.so")
+LIB_PATH = os.environ.get("LIBBNR", os.path.join(_HERE, "libbnr.so"))   # LIBBNR: alternative build (debugging)
 
 
 class BnrError(RuntimeError):

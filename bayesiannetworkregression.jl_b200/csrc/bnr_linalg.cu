@@ -356,9 +356,15 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     }
     return;
   }
+  // At least 4 row fragments per warp (8 DMMAs per k4-step).  With a single fragment the panel solve (MODE 2: no
+  // scaling DMUL between the fragment loads and the two DMMAs of a step) returned deterministic wrong sums on B200 --
+  // k-steps of a recycled ring stage counted twice -- while 2 and more fragments, and the scaled MODE 0 loop with one
+  // fragment, are exact (scratch/dbg128.py); the cause was not isolated, so the tight 2-DMMA loop is simply not
+  // instantiated.  The extra fragments are rows of the zero padding: a few wasted DMMAs in the last row block only.
+  if (nfv < 4) nfv = 4;
   switch (nfv) {
 #define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
-    BNR_STRIP_CASE(1) BNR_STRIP_CASE(2) BNR_STRIP_CASE(3) BNR_STRIP_CASE(4) BNR_STRIP_CASE(5) BNR_STRIP_CASE(6)
+    BNR_STRIP_CASE(4) BNR_STRIP_CASE(5) BNR_STRIP_CASE(6)
     BNR_STRIP_CASE(7) BNR_STRIP_CASE(8) BNR_STRIP_CASE(9) BNR_STRIP_CASE(10) BNR_STRIP_CASE(11) BNR_STRIP_CASE(12)
     BNR_STRIP_CASE(13) BNR_STRIP_CASE(14) BNR_STRIP_CASE(15)
 #undef BNR_STRIP_CASE

@@ -288,18 +288,26 @@ def test_lambda_pi(small):
 
 @pytest.mark.parametrize("V,R,n,dense,mode", [(7, 4, 23, True, "nform"), (12, 5, 150, False, "nform"),
                                               (20, 7, 300, True, "nform"), (7, 4, 23, True, "qform"),
-                                              (18, 5, 150, False, "qform"), (22, 7, 300, True, "qform")])
+                                              (18, 5, 150, False, "qform"), (22, 7, 300, True, "qform"),
+                                              # edge cases: smallest network, single sample, n a multiple of 128
+                                              # (extra padding block for the bordering row), R at its maximum
+                                              (2, 1, 3, True, "nform"), (3, 2, 1, True, "nform"), (2, 1, 5, True, "qform"),
+                                              (6, 3, 128, True, "nform"), (4, 16, 30, True, "qform")])
 def test_full_sweeps_injected(bnr, V, R, n, dense, mode):
     """bnr_run (production schedule, fused kernels) == oracle gibbs_sweep for consecutive sweeps; the larger
     cases span several 128-row tiles and 64-column Cholesky panels."""
     C, K = 2, 64
     X, y = make_problem(V * 100 + n, V, R, n, dense)
     rng = np.random.default_rng(V)
-    with bnr.Engine(X, y, R, num_chains=C, seed=1, gig_inject_len=K, trace_rows=4, gamma_mode=mode) as eng:
+    hyper = dict(O.DEFAULT_HYPER)
+    if R > 9:
+        hyper["nu"] = R + 4              # InverseWishart needs nu > R - 1
+    with bnr.Engine(X, y, R, num_chains=C, seed=1, gig_inject_len=K, trace_rows=4, gamma_mode=mode,
+                    nu=hyper["nu"]) as eng:
         init = np.stack([_init_injection(rng, V, R) for _ in range(C)])
         eng.set_injection(init)
         eng.init_state()
-        sts = [O.initialize_state(V, R, O.DEFAULT_HYPER, init[c]) for c in range(C)]
+        sts = [O.initialize_state(V, R, hyper, init[c]) for c in range(C)]
         for c in range(C):
             got = eng.get_state_dict(c)
             for k in sts[c]:
@@ -309,7 +317,7 @@ def test_full_sweeps_injected(bnr, V, R, n, dense, mode):
             eng.set_injection(inj)
             eng.run(1)
             for c in range(C):
-                new, aux = O.gibbs_sweep(sts[c], X, y, V, R, O.DEFAULT_HYPER, inj[c], K, literal=False,
+                new, aux = O.gibbs_sweep(sts[c], X, y, V, R, hyper, inj[c], K, literal=False,
                                          gamma_form="q" if mode == "qform" else "n")
                 cond = np.linalg.cond(aux["gamma"]["P" if mode == "qform" else "G"])
                 got = eng.get_state_dict(c)
