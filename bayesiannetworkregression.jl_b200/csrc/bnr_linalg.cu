@@ -72,6 +72,9 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // The per-chain scale s_c[k] is applied to the operand with the fewest fragments per warp (2): DMUL shares the
 // FP64 pipe with DMMA.  Work that cannot contribute is skipped: the symmetric half of diagonal tiles and row
 // fragments that lie entirely in the zero padding beyond n.
+// NOTE the ring is written by the TMA engine behind the compiler's back: the consumer-side pointers into it must NOT
+// be __restrict__ (with a compile-time trip count the compiler then reuses the fragments of a stage's previous
+// occupant); the "memory" clobber of mbar_wait is what orders the fragment loads after the hand-shake.
 // grid = (C, tiles), block = 384 (2 consumer warpgroups + 1 producer warpgroup, registers re-balanced with
 // setmaxnreg: 232 per consumer thread, 40 per producer thread); dynamic smem = SYRK_SMEM.
 // ------------------------------------------------------------------------------------------------------------
@@ -91,7 +94,7 @@ constexpr size_t SYRK_SMEM = (size_t)SY_STAGES * SY_STAGE_DBL * sizeof(double) +
 // parameter: every loop bound and register index is static, no predicated DMMA.
 // acc[t], t < 16-W : fragment (row-fragment W+t, column-fragment W);  t >= 16-W : (row-fragment t-1, column 15-W).
 template <int MODE, int W>
-__device__ __forceinline__ void syrk_diag_frags(const double* __restrict__ sj, const double* __restrict__ ss, int k4,
+__device__ __forceinline__ void syrk_diag_frags(const double* sj, const double* ss, int k4,
                                                 int lk, int lr, double (&a2)[2], double (&bfr)[16 - W]) {
   const int kr = k4 * 4 + lk;
   const double* row = sj + kr * SY_LDS + lr;
@@ -110,7 +113,7 @@ __device__ __forceinline__ void syrk_diag_frags(const double* __restrict__ sj, c
 }
 
 template <int MODE, int W>
-__device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, unsigned long long* full,
+__device__ __forceinline__ void syrk_diag_tile(const double* smem, unsigned long long* full,
                                                unsigned long long* empty, int nk, int lk, int lr, int lane,
                                                double* __restrict__ Cc, int np, int i0, double diag_add) {
   constexpr int NA = 16 - W;        // fragments of column W
@@ -167,8 +170,8 @@ __device__ __forceinline__ void syrk_diag_tile(const double* __restrict__ smem, 
 // fragments, (b) lets a tile of the last block row stop at the last fragment that holds a valid row (NF < 16):
 // the zero padding of n up to a multiple of 128 costs no tensor work.
 template <int MODE, int NF>
-__device__ __forceinline__ void syrk_strip_frags(const double* __restrict__ sj, const double* __restrict__ si,
-                                                 const double* __restrict__ ss, int k4, int warp, int lk, int lr,
+__device__ __forceinline__ void syrk_strip_frags(const double* sj, const double* si, const double* ss, int k4,
+                                                 int warp, int lk, int lr,
                                                  double (&af)[2], double (&bf)[NF]) {
   const int kr = k4 * 4 + lk;
   const double* rj = sj + kr * SY_LDS + warp * 16 + lr;
@@ -186,7 +189,7 @@ __device__ __forceinline__ void syrk_strip_frags(const double* __restrict__ sj, 
 }
 
 template <int MODE, int NF>
-__device__ __forceinline__ void syrk_strip_tile(const double* __restrict__ smem, unsigned long long* full,
+__device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned long long* full,
                                                 unsigned long long* empty, int nk, int warp, int lk, int lr, int lane,
                                                 double* __restrict__ Cc, int np, int i0, int j0) {
   double acc[2][NF][2];
@@ -356,11 +359,7 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     }
     return;
   }
-  // At least 4 row fragments per warp (8 DMMAs per k4-step).  With a single fragment the panel solve (MODE 2: no
-  // scaling DMUL between the fragment loads and the two DMMAs of a step) returned deterministic wrong sums on B200 --
-  // k-steps of a recycled ring stage counted twice -- while 2 and more fragments, and the scaled MODE 0 loop with one
-  // fragment, are exact (scratch/dbg128.py); the cause was not isolated, so the tight 2-DMMA loop is simply not
-  // instantiated.  The extra fragments are rows of the zero padding: a few wasted DMMAs in the last row block only.
+  // (at least 4 row fragments: fewer template instances; the extra fragments are zero-padding rows of the last block)
   if (nfv < 4) nfv = 4;
   switch (nfv) {
 #define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
