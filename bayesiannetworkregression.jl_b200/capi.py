@@ -19,7 +19,7 @@ class Params(C.Structure):
                 ("trace_gamma_xi_all", C.c_int32), ("trace_rows", C.c_int64), ("seed", C.c_uint64),
                 ("eta", C.c_double), ("zeta", C.c_double), ("iota", C.c_double), ("a_delta", C.c_double),
                 ("b_delta", C.c_double), ("nu", C.c_double), ("gig_inject_len", C.c_int32),
-                ("gamma_mode", C.c_int32), ("chain_groups", C.c_int32), ("reserved", C.c_int32)]
+                ("gamma_mode", C.c_int32), ("chain_groups", C.c_int32), ("trace_gamma_xi_chains", C.c_int32)]
 
 
 VAR = dict(tau2=0, u=1, xi=2, gamma=3, S=4, theta=5, Delta=6, M=7, mu=8, lam=9, pi=10)

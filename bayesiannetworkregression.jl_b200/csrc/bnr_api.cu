@@ -247,7 +247,11 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   DA(h->d_rhat, (size_t)(d.V + d.q));
   e.trace_full_chains = p->trace_rows > 0 ? (p->trace_full_chains < d.C ? p->trace_full_chains : d.C) : 0;
   if (e.trace_full_chains < 0) e.trace_full_chains = 0;
-  e.trace_gx_all = (p->trace_rows > 0 && p->trace_gamma_xi_all) ? 1 : 0;
+  e.trace_gx_chains = 0;
+  if (p->trace_rows > 0) {
+    if (p->trace_gamma_xi_all) e.trace_gx_chains = d.C;
+    else if (p->trace_gamma_xi_chains > 0) e.trace_gx_chains = p->trace_gamma_xi_chains < d.C ? p->trace_gamma_xi_chains : d.C;
+  }
   e.trace_rows = p->trace_rows > 0 ? p->trace_rows : 0;
   e.rowlen_full = 4 + d.V * d.R + d.V + 2 * d.q + d.R * d.R + d.R + 3 * d.R;
   e.tr_full = nullptr; e.tr_gx = nullptr;
@@ -255,8 +259,8 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
     int r = dalloc(h, &e.tr_full, (size_t)e.trace_full_chains * e.trace_rows * e.rowlen_full, false);
     if (r) return r;
   }
-  if (e.trace_gx_all) {
-    int r = dalloc(h, &e.tr_gx, C * e.trace_rows * (d.V + d.q), false);
+  if (e.trace_gx_chains > 0) {
+    int r = dalloc(h, &e.tr_gx, (size_t)e.trace_gx_chains * e.trace_rows * (d.V + d.q), false);
     if (r) return r;
   }
   {
@@ -396,7 +400,11 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   v.G += c * d.gdim * d.gdim; if (v.syrk_ws) v.syrk_ws += c * (size_t)v.syrk_ws_cap * d.gdim * d.gdim; v.Linv += c * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N;
   v.partials += c * d.nparts * (2 * MAX_R + 1);
   v.moments += c * 2 * (d.V + d.q) * 2;
+  int tgc = h->e.trace_gx_chains - c0;
+  tgc = tgc < 0 ? 0 : (tgc > Cg ? Cg : tgc);
+  v.trace_gx_chains = tgc;
   if (v.tr_gx) v.tr_gx += c * v.trace_rows * (d.V + d.q);
+  if (tgc == 0) v.tr_gx = nullptr;
   int tfc = h->e.trace_full_chains - c0;
   tfc = tfc < 0 ? 0 : (tfc > Cg ? Cg : tfc);
   v.trace_full_chains = tfc;
@@ -554,7 +562,7 @@ extern "C" int bnr_copy_trace_rows(bnr_handle* h, int64_t dst, int64_t src, int6
     return 0;
   };
   if (e.tr_full) { int r = move(e.tr_full, e.rowlen_full, e.trace_full_chains); if (r) return r; }
-  if (e.tr_gx) { int r = move(e.tr_gx, e.d.V + e.d.q, e.d.C); if (r) return r; }
+  if (e.tr_gx) { int r = move(e.tr_gx, e.d.V + e.d.q, e.trace_gx_chains); if (r) return r; }
   CK(cudaStreamSynchronize(h->stream));
   return BNR_OK;
 }
@@ -616,7 +624,9 @@ __global__ void k_moments_from_trace(const double* __restrict__ tr, long long tr
 extern "C" int bnr_moments_from_trace(bnr_handle* h, int64_t first_row, int64_t nrows) {
   if (!h || first_row < 0 || nrows < 0) return fail(BNR_EINVAL, "bad arguments");
   Engine& e = h->e;
-  if (!e.tr_gx) return fail(BNR_ESTATE, "gamma/xi traces are not recorded (trace_gamma_xi_all = 0)");
+  if (!e.tr_gx || e.trace_gx_chains < e.d.C)
+    return fail(BNR_ESTATE, "gamma/xi traces of every chain are needed (trace_gamma_xi_all = 0): use the streaming "
+                            "moments of bnr_set_moment_window instead");
   if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
   if (nrows / 2 < 2) return fail(BNR_EINVAL, "need at least 4 rows");
   const int np_ = e.d.V + e.d.q;
@@ -726,7 +736,7 @@ extern "C" int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t 
     rowlen = e.rowlen_full;
     rows = e.tr_full + (size_t)chain * e.trace_rows * rowlen;
     off = row_offset(d, var);
-  } else if (e.tr_gx && (var == BNR_VAR_XI || var == BNR_VAR_GAMMA)) {
+  } else if (e.tr_gx && chain < e.trace_gx_chains && (var == BNR_VAR_XI || var == BNR_VAR_GAMMA)) {
     rowlen = d.V + d.q;
     rows = e.tr_gx + (size_t)chain * e.trace_rows * rowlen;
     off = var == BNR_VAR_XI ? 0 : d.V;
@@ -964,7 +974,7 @@ extern "C" int bnr_summary(bnr_handle* h, int32_t chain, int64_t first_row, int6
     rowlen = e.rowlen_full;
     rows = e.tr_full + (size_t)chain * e.trace_rows * rowlen;
     off_g = row_offset(d, BNR_VAR_GAMMA); off_x = row_offset(d, BNR_VAR_XI);
-  } else if (e.tr_gx) {
+  } else if (e.tr_gx && chain < e.trace_gx_chains) {
     rowlen = d.V + d.q;
     rows = e.tr_gx + (size_t)chain * e.trace_rows * rowlen;
     off_g = d.V; off_x = 0;
@@ -993,7 +1003,8 @@ extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrow
   if (!h || first_row < 0 || nrows < 4 || max_lag < 1) return fail(BNR_EINVAL, "bad arguments (need nrows >= 4, max_lag >= 1)");
   Engine& e = h->e;
   const Dims& d = e.d;
-  if (!e.tr_gx) return fail(BNR_ESTATE, "gamma/xi traces are not recorded (trace_gamma_xi_all = 0)");
+  if (!e.tr_gx || e.trace_gx_chains < d.C)
+    return fail(BNR_ESTATE, "gamma/xi traces of every chain are not recorded (trace_gamma_xi_all = 0)");
   if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
   if (max_lag > nrows - 1) max_lag = (int32_t)(nrows - 1);
   if (!(max_lag & 1)) max_lag -= 1;                  // Geyer pairs (2t, 2t+1): keep the last lag odd

@@ -114,9 +114,9 @@ struct Engine {
   double* moments;
   long long* mom_window;  // device [2]: first sweep, len
   // traces
-  int trace_full_chains; int trace_gx_all; long long trace_rows;
+  int trace_full_chains; int trace_gx_chains; long long trace_rows;   // leading chains with full / (xi, gamma) rows
   double* tr_full;  // [trace_full_chains][rows][rowlen_full]
-  double* tr_gx;    // [C][rows][V+q]  (xi then gamma), only when trace_gx_all
+  double* tr_gx;    // [trace_gx_chains][rows][V+q]  (xi then gamma)
   int rowlen_full;
   // injection
   const double* inj;  // [C][inj_stride] or nullptr

@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(256) k_record(Engine e, int sweep_done /* 1: s
   const int np_ = d.V + d.q;
   if (p < np_) {
     const double x = (p < d.V) ? e.xi[c * d.V + p] : e.gamma[(size_t)c * d.qp + (p - d.V)];
-    if (e.tr_gx && row < e.trace_rows) e.tr_gx[((size_t)c * e.trace_rows + row) * np_ + p] = x;
+    if (e.tr_gx && c < e.trace_gx_chains && row < e.trace_rows) e.tr_gx[((size_t)c * e.trace_rows + row) * np_ + p] = x;
     const long long first = e.mom_window[0], len = e.mom_window[1];
     const long long h = len / 2, rel = sweep - first;
     if (len > 1 && rel >= 0 && rel < len) {

@@ -19,7 +19,7 @@ class Engine:
 
     def __init__(self, X, y, R, num_chains=2, seed=0, chain_offset=0, device=0, trace_rows=0,
                  trace_full_chains=1, trace_gamma_xi_all=True, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0,
-                 b_delta=1.0, nu=10.0, gig_inject_len=64, gamma_mode="auto", chain_groups=0):
+                 b_delta=1.0, nu=10.0, gig_inject_len=64, gamma_mode="auto", chain_groups=0, trace_gamma_xi_chains=0):
         X = np.asarray(X, dtype=np.float64)
         y = np.ascontiguousarray(y, dtype=np.float64)
         if X.ndim != 2 or y.ndim != 1 or X.shape[0] != y.shape[0]:
@@ -41,6 +41,7 @@ class Engine:
         p.gig_inject_len = int(gig_inject_len)
         p.gamma_mode = GAMMA_MODE[gamma_mode] if isinstance(gamma_mode, str) else int(gamma_mode)
         p.chain_groups = int(chain_groups)
+        p.trace_gamma_xi_chains = int(trace_gamma_xi_chains)
         self.params = p
         self.device = int(device)
         self.trace_rows = int(trace_rows)

@@ -140,12 +140,21 @@ def _run_rows(eng, first_index, nburn, total, purge_burn):
         eng.run(seg_len)
 
 
-def _psrf(eng, nb, nsamp):
-    """return_psrf_VOI (src/gibbs.jl:771-789): R-hat over table rows nb+1 .. nb+nsamp of every chain."""
+def _psrf(eng, nb, nsamp, streamed=False):
+    """return_psrf_VOI (src/gibbs.jl:771-789): R-hat over table rows nb+1 .. nb+nsamp of every chain.
+    streamed: the split-half moments of exactly those draws were accumulated while the chains ran
+    (bnr_set_moment_window), so no chain but the first needs a trace."""
     if nsamp // 2 < 2:
         return np.full(eng.V, np.nan), np.full(eng.q, np.nan)
-    eng.moments_from_trace(nb, nsamp)
+    if not streamed:
+        eng.moments_from_trace(nb, nsamp)
     return eng.rhat()
+
+
+def _stream_last(eng, new_sweeps, nsamp):
+    """Arm the streaming moments for the last nsamp of the next `new_sweeps` sweeps (the rows the PSRF will use)."""
+    s_end = eng.iteration + new_sweeps
+    eng.set_moment_window(s_end - nsamp + 1, nsamp)
 
 
 def _fetch_state(eng, rows, what):
@@ -247,15 +256,21 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
     purge_burn = _normalise_purge(purge_burn, nburn)
     tot_save = total if purge_burn is None else nsamp + purge_burn
     seed = random.randint(1, 55555) if seed is None else seed
+    # R-hat needs the retained draws of EVERY chain.  Whenever those draws are always newly generated ones
+    # (nburn >= nsamp, and the purge ring leaves room) their split-half moments are streamed on the device and only
+    # chain 1 keeps a trace: memory is one chain's table instead of num_chains tables.
+    streamed = nburn >= nsamp and nsamp >= 1 and (purge_burn is None or nsamp + purge_burn <= nburn)
     eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, trace_rows=tot_save,
-                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=True,
-                 eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
+                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=not streamed,
+                 trace_gamma_xi_chains=1, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
     try:
         eng.init_state()
+        if streamed:
+            _stream_last(eng, total - 1, nsamp)
         _run_rows(eng, 2, nburn, total, purge_burn)
         nb = purge_burn if purge_burn is not None else nburn
         tot_generated = nburn + nsamp
-        rx, rg = _psrf(eng, nb, nsamp)
+        rx, rg = _psrf(eng, nb, nsamp, streamed)
         if verbose:
             print("%d samples generated. Max PSRF XI: %.2f. Max PSRF Gamma: %.2f" % (tot_generated, _max(rx), _max(rg)))
         while (_max(rx) > psrf_cutoff or _max(rg) > psrf_cutoff) and tot_generated < maxburn + nsamp:
@@ -265,9 +280,11 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
                 num2move = total - nburn
             eng.copy_trace_rows(0, tot_save - num2move, num2move)
             a_total = num2move + nburn if num2move > 1 else nburn
+            if streamed:
+                _stream_last(eng, a_total - num2move, nsamp)
             _run_rows(eng, num2move + 1, (nburn - nsamp + num2move) if nburn > nsamp else 0, a_total, purge_burn)
             tot_generated += a_total - num2move
-            rx, rg = _psrf(eng, nb, nsamp)
+            rx, rg = _psrf(eng, nb, nsamp, streamed)
             if verbose:
                 print("%d samples generated. Max PSRF XI: %.3f. Max PSRF Gamma: %.3f" %
                       (tot_generated, _max(rx), _max(rg)))
@@ -275,7 +292,7 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
             engine_hook(eng)
         state = _fetch_state(eng, tot_save, return_state)
         extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
-                     device_summary=_device_summary(eng, nb, nsamp))
+                     device_summary=_device_summary(eng, nb, nsamp), rhat_streamed=streamed)
         return Results(state, rx, rg, nb, nsamp, extra)
     finally:
         eng.close()

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BNR_VERSION 101
+#define BNR_VERSION 102
 
 /* error codes */
 #define BNR_OK 0
@@ -120,7 +120,8 @@ typedef struct bnr_params {
   int32_t gamma_mode;        /* BNR_GAMMA_AUTO (cost model) | BNR_GAMMA_NFORM | BNR_GAMMA_QFORM              */
   int32_t chain_groups;      /* chain groups advanced by independent streams/graphs (0 = default 2, max 4);
                                 a throughput knob only: results are identical for every value               */
-  int32_t reserved;
+  int32_t trace_gamma_xi_chains; /* when trace_gamma_xi_all == 0: leading local chains whose gamma / xi rows are
+                                    recorded (chain 1 is all Results / Summary need when R-hat is streamed)    */
 } bnr_params;
 
 /* Formulation of the gamma draw (update_gamma!, src/gibbs.jl:420-438).  Both sample the same conditional

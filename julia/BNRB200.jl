@@ -15,7 +15,7 @@ struct BnrParams
     chain_offset::Int32; device::Int32; trace_full_chains::Int32; trace_gamma_xi_all::Int32
     trace_rows::Int64; seed::UInt64
     eta::Float64; zeta::Float64; iota::Float64; a_delta::Float64; b_delta::Float64; nu::Float64
-    gig_inject_len::Int32; gamma_mode::Int32; chain_groups::Int32; reserved::Int32
+    gig_inject_len::Int32; gamma_mode::Int32; chain_groups::Int32; trace_gamma_xi_chains::Int32
 end
 
 function check(code::Cint)

@@ -151,8 +151,26 @@ def test_fit_purge_burn_and_extension(bnr):
     assert len(a.state) == 70 and len(b.state) == 40 and b.burn_in == 10
     np.testing.assert_array_equal(a.state["γ"][40:70], b.state["γ"][10:40])
     np.testing.assert_array_equal(a.rhatγ.γ, b.rhatγ.γ)
+    assert a.extra["rhat_streamed"] and b.extra["rhat_streamed"]
+    # the streamed split-half moments give the R-hat of exactly rows nburn+1 .. nburn+nsamp of every chain
+    with bnr.Engine(X, y, 3, num_chains=2, seed=3, trace_rows=70) as eng:
+        eng.init_state()
+        eng.run(69)
+        eng.moments_from_trace(40, 30)
+        rx, rg = eng.rhat()
+    np.testing.assert_allclose(a.rhatγ.γ, rg, rtol=1e-9)
+    fin = np.isfinite(rx)
+    np.testing.assert_allclose(a.rhatξ.ξ[fin], rx[fin], rtol=1e-9)
+    e = bnr.Fit(X, y, 3, psrf_cutoff=1e9, nburn=20, nsamples=30, num_chains=2, seed=3, x_transform=False, filename=None)
+    assert not e.extra["rhat_streamed"] and len(e.state) == 50          # nburn < nsamp: trace-based R-hat
     c = bnr.Fit(X, y, 3, psrf_cutoff=0.0, **kw)       # never "converged"
     assert c.extra["tot_generated"] == 70 + 40 and len(c.state) == 70
+    with bnr.Engine(X, y, 3, num_chains=2, seed=3, trace_rows=110) as eng:     # 69 + 40 sweeps, last 30 retained
+        eng.init_state()
+        eng.run(109)
+        eng.moments_from_trace(80, 30)
+        _, rg2 = eng.rhat()
+    np.testing.assert_allclose(c.rhatγ.γ, rg2, rtol=1e-9)
     np.testing.assert_array_equal(c.state["γ"][:30], a.state["γ"][40:70])   # old samples moved to the front
     d = bnr.Fit(X, y, 3, mingen=40, maxgen=120, psrf_cutoff=0.0, num_chains=2, seed=3, x_transform=False,
                 filename=None)
