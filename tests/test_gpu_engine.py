@@ -484,3 +484,27 @@ def test_syrk_split_k_path(bnr):
             outs.append(eng.get_state(1, "gamma").copy())
             assert not (eng.status() & ~1).any()
     np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_config2_qform_matches_nform_and_oracle_chain():
+    """BASELINE config 2 (V=30, n=500, R=7, 16 chains; the cost model runs the q x q form): node-inclusion
+    probabilities of the GPU sampler in both gamma formulations and of the CPU oracle chain agree within Monte-Carlo
+    error on the benchmark's own synthetic data."""
+    import bench
+    from __graft_entry__ import load_package
+    bnr = load_package()
+    X, y, dims = bench.synth("c2")
+    X = np.ascontiguousarray(X)
+    V, R = dims["V"], dims["R"]
+    prob = {}
+    for mode in ("auto", "nform"):
+        with bnr.Engine(X, y, R, num_chains=16, seed=5, trace_rows=6001, trace_full_chains=0, gamma_mode=mode) as eng:
+            assert eng.gamma_mode == ("qform" if mode == "auto" else "nform")
+            eng.init_state()
+            eng.run(6000)
+            prob[mode] = np.mean([eng.get_trace(c, "xi", 3001, 6001)[:, :, 0].mean(axis=0) for c in range(16)], axis=0)
+            assert not (eng.status() & ~1).any()
+    ora = np.mean([OC.run_chain(X, y, R, 1600, seed=s_, record=("xi",))[0]["xi"][601:].reshape(-1, V).mean(axis=0)
+                   for s_ in (1, 2)], axis=0)
+    assert np.abs(prob["auto"] - prob["nform"]).max() < 0.03
+    assert np.abs(prob["auto"] - ora).max() < 0.07
