@@ -79,9 +79,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // setmaxnreg: 232 per consumer thread, 40 per producer thread); dynamic smem = SYRK_SMEM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SY_BT = 128;        // tile edge
-constexpr int SY_BK = 16;         // k-step
+#ifndef BNR_SY_BK
+#define BNR_SY_BK 16
+#endif
+#ifndef BNR_SY_STAGES
+#define BNR_SY_STAGES 4
+#endif
+constexpr int SY_BK = BNR_SY_BK;  // k-step
 constexpr int SY_LDS = 132;       // smem row stride in doubles (== 4 mod 16 -> conflict-free fragment loads)
-constexpr int SY_STAGES = 4;
+constexpr int SY_STAGES = BNR_SY_STAGES;
 constexpr int SYRK_MAX_SPLITS = 8;
 constexpr int SY_STAGE_DBL = 2 * SY_BK * SY_LDS + SY_BK;   // two operand tiles + 16 scales
 constexpr int SY_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgroup (one active lane)
@@ -443,9 +449,6 @@ k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int
 //     shared-memory ring, 64-column half blocks), every step is a block mat-vec; the diagonal blocks use Linv.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;            // panel / diagonal block size
-constexpr int XD_LD = 34;          // column stride of the 32 x 32 scratch blocks (even: 16-byte loads; 34: spreads banks)
-constexpr int XD_BLK = 32 * XD_LD;
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PB + 9 * XD_BLK + PB + 64) + 16;
 constexpr int CHOL_MAX_DIM = 4096; // largest factored dimension (shared-memory solution vector of the back solve)
 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
@@ -489,33 +492,38 @@ __global__ void __launch_bounds__(256) k_augment(double* __restrict__ G, size_t 
   }
 }
 
-// 4 rows x 2 columns of a product of 32 x 32 blocks: acc += Aop[r4 .. r4+3][p] * Bop[p][c2 .. c2+1], p = 0..31
-// (both operands column-major with the given column strides; Aop rows must be 16-byte aligned)
-__device__ __forceinline__ void blk32_fma(double (&acc)[4][2], const double* __restrict__ Aop, int lda,
-                                          const double* __restrict__ Bop, int ldb, int r4, int c2) {
-#pragma unroll 8
-  for (int p = 0; p < 32; ++p) {
-    const double2 a01 = *reinterpret_cast<const double2*>(Aop + p * lda + r4);
-    const double2 a23 = *reinterpret_cast<const double2*>(Aop + p * lda + r4 + 2);
-    const double b0 = Bop[c2 * ldb + p], b1 = Bop[(c2 + 1) * ldb + p];
-    acc[0][0] += a01.x * b0; acc[0][1] += a01.x * b1;
-    acc[1][0] += a01.y * b0; acc[1][1] += a01.y * b1;
-    acc[2][0] += a23.x * b0; acc[2][1] += a23.x * b1;
-    acc[3][0] += a23.y * b0; acc[3][1] += a23.y * b1;
+// ---- warp-level 32 x 32 x 32 products on the FP64 tensor cores, operands column-major in shared memory ----
+// One 8 x 8 output fragment of C = A B (A, B 32 x 32, leading dimensions lda / ldb == 4 mod 16 doubles -> conflict-free):
+// the MMA runs on the transposed problem (M along the columns n of C, N along its rows m), so that the accumulator pair
+// of a lane is rows m0 + 2 lk, + 1 of column n0 + lr -> one 16-byte store.   acc += A[m0.., :] B[:, n0..]
+__device__ __forceinline__ void frag_mm32(double& c0, double& c1, const double* Aop, int lda, const double* Bop, int ldb,
+                                          int m0, int n0, int lk, int lr) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const int k = k4 * 4 + lk;
+    const double bt = Bop[(n0 + lr) * ldb + k];       // "A" operand of the transposed problem: B'[n][k]
+    const double at = Aop[k * lda + m0 + lr];         // "B" operand: A'[k][m]
+    dmma884(c0, c1, bt, at);
   }
 }
+
+constexpr int PLD = 132;           // column stride of the 128 x 128 working block (== 4 mod 16: conflict-free fragments)
+constexpr int XD_LD = 36;          // column stride of the 32 x 32 scratch blocks (== 4 mod 16)
+constexpr int XD_BLK = 32 * XD_LD;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 9 * XD_BLK + PB + 64) + 16;
 
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_t chain_stride, int N, int J,
                                                    double* __restrict__ Linv, int T, int* status) {
   extern __shared__ __align__(16) double sm[];
-  double* A = sm;                          // column-major 128 x 128 working block: A[col * PB + row]
-  double* Xd = sm + PB * PB;               // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
+  double* A = sm;                          // column-major 128 x 128 working block: A[col * PLD + row]
+  double* Xd = sm + PB * PLD;              // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
   double* Tm = Xd + 4 * XD_BLK;            // [4] intermediate products of the inverse
-  double* X10s = Tm + 4 * XD_BLK;          // [1] copy of the (1,0) inverse block with the conflict-free stride
+  double* X10s = Tm + 4 * XD_BLK;          // [1] spare block
   double* dall = X10s + XD_BLK;            // [128] reciprocal diagonal of L
   double* Lcol = dall + PB;                // [2][32] current column of the 32 x 32 factorisation (double-buffered)
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lk = lane & 3, lr = lane >> 2;
   double* D = G + (size_t)c * chain_stride + (size_t)J * PB * N + (size_t)J * PB;
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(bar, PB * PB * 8);
-    for (int col = 0; col < PB; ++col) bulk_g2s(A + col * PB, D + (size_t)col * N, PB * 8, bar);
+    for (int col = 0; col < PB; ++col) bulk_g2s(A + col * PLD, D + (size_t)col * N, PB * 8, bar);
   }
   mbar_wait(bar, 0);
   bool bad = false;
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
       // its rsqrt chain runs under the remaining updates of column j.
       double a[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = A[(o + j) * PB + o + lane];
+      for (int j = 0; j < 32; ++j) a[j] = A[(o + j) * PLD + o + lane];
       double djj = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -558,49 +566,48 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (lane >= j) A[(o + j) * PB + o + lane] = a[j];
+        if (lane >= j) A[(o + j) * PLD + o + lane] = a[j];
     }
     __syncthreads();
     // rows below: x L_ss' = a, thread per row, right-looking (independent FMAs, broadcast reads of L_ss)
     const int nbelow = PB - (o + 32);
     if (tid < nbelow) {
-      double* row = A + o * PB + o + 32 + tid;
+      double* row = A + o * PLD + o + 32 + tid;
       double x[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = row[j * PB];
+      for (int j = 0; j < 32; ++j) x[j] = row[j * PLD];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const double xj = x[j] * dall[o + j];
         x[j] = xj;
 #pragma unroll
-        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PB + o + k];
+        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PLD + o + k];
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) row[j * PB] = x[j];
+      for (int j = 0; j < 32; ++j) row[j * PLD] = x[j];
     }
     __syncthreads();
-    // trailing update in 2 x 2 register tiles: A[r][cc] -= sum_p L[r][o+p] L[cc][o+p], o+32 <= cc <= r
-    const int base = o + 32;
-    const int n2 = (PB - base) / 2;              // row / column pairs
-    for (int id = tid; id < n2 * n2; id += 256) {
-      const int r = base + 2 * (id % n2), cc = base + 2 * (id / n2);
-      if (cc > r) continue;
-      double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
-#pragma unroll 8
-      for (int p = 0; p < 32; ++p) {
-        const double2 lr2 = *reinterpret_cast<const double2*>(A + (o + p) * PB + r);
-        const double2 lc2 = *reinterpret_cast<const double2*>(A + (o + p) * PB + cc);
-        s00 += lr2.x * lc2.x; s01 += lr2.x * lc2.y; s10 += lr2.y * lc2.x; s11 += lr2.y * lc2.y;
+    // trailing update on the tensor cores: A[r][cc] -= sum_p L[r][o+p] L[cc][o+p] for o+32 <= cc <= r, by 8 x 8
+    // fragments of the lower triangle (diagonal fragments are computed whole; what lands above the diagonal is
+    // never read).  Fragment (fr, fc), fc <= fr; the warps take them round-robin.
+    {
+      const int base = o + 32, nf = (PB - base) / 8, nfrag = nf * (nf + 1) / 2;
+      const double* P = A + o * PLD + base;           // panel: P[p * PLD + i] = L[base + i][o + p]
+      for (int f = warp; f < nfrag; f += 8) {
+        int fr = 0;
+        while ((fr + 1) * (fr + 2) / 2 <= f) ++fr;
+        const int fc = f - fr * (fr + 1) / 2;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const int k = k4 * 4 + lk;
+          dmma884(c0, c1, P[k * PLD + fc * 8 + lr], P[k * PLD + fr * 8 + lr]);   // M along the column index cc
+        }
+        double2* dst = reinterpret_cast<double2*>(A + (base + fc * 8 + lr) * PLD + base + fr * 8 + 2 * lk);
+        double2 v = *dst;
+        v.x -= c0; v.y -= c1;
+        *dst = v;
       }
-      double2* p0 = reinterpret_cast<double2*>(A + cc * PB + r);
-      double2 v = *p0;
-      v.x -= s00; v.y -= s10;
-      *p0 = v;
-      double2* p1 = reinterpret_cast<double2*>(A + (cc + 1) * PB + r);
-      v = *p1;
-      if (cc + 1 <= r) v.x -= s01;
-      v.y -= s11;
-      *p1 = v;
     }
     __syncthreads();
   }
@@ -609,7 +616,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   fence_async_smem();
   __syncthreads();
   if (tid == 0) {
-    for (int col = 0; col < PB; ++col) bulk_s2g(D + (size_t)col * N, A + col * PB, PB * 8);
+    for (int col = 0; col < PB; ++col) bulk_s2g(D + (size_t)col * N, A + col * PLD, PB * 8);
     bulk_commit();
     bulk_wait_read0();
   }
@@ -625,7 +632,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
       const double xk = x[k] * dall[o + k];
       x[k] = xk;
 #pragma unroll
-      for (int i = k + 1; i < 32; ++i) x[i] -= A[(o + k) * PB + o + i] * xk;
+      for (int i = k + 1; i < 32; ++i) x[i] -= A[(o + k) * PLD + o + i] * xk;
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) Xd[b * XD_BLK + j * XD_LD + i] = (i >= j) ? x[i] : 0.0;
@@ -633,77 +640,68 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   __syncthreads();   // also orders the bulk-store reads (tid 0 waited above) before the in-place overwrite below
   // (2) off-diagonal 32 x 32 blocks of the inverse by the recursive 2 x 2 block formula
   //        [[A, 0], [C, B]]^-1 = [[A^-1, 0], [-B^-1 C A^-1, B^-1]],
-  //     first inside the two 64 x 64 diagonal blocks, then for the 64 x 64 block below them.  Every stage is a set of
-  //     32 x 32 x 32 products with the same cost per thread (4 x 2 register tiles, one or two tasks per thread).
-  //     Operands that are read column-wise (the right factors) sit in the stride-34 scratch blocks.
-  auto blkA = [&](int i, int j) { return A + (32 * j) * PB + 32 * i; };        // block (i, j) of the working matrix
-  {
-    // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1      stage 2: X_(2b+1, 2b) = -Xd_(2b+1) T_b
-    const int b = tid >> 7, tt = tid & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2;
-    double acc[4][2] = {};
-    blk32_fma(acc, blkA(2 * b + 1, 2 * b), PB, Xd + (2 * b) * XD_BLK, XD_LD, r4, c2);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      Tm[b * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
-      Tm[b * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
-    }
-    __syncthreads();
-    double acc2[4][2] = {};
-    blk32_fma(acc2, Xd + (2 * b + 1) * XD_BLK, XD_LD, Tm + b * XD_BLK, XD_LD, r4, c2);
-    double* dst = blkA(2 * b + 1, 2 * b) + c2 * PB + r4;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      dst[a] = -acc2[a][0];
-      dst[PB + a] = -acc2[a][1];
-      if (b == 0) { X10s[c2 * XD_LD + r4 + a] = -acc2[a][0]; X10s[(c2 + 1) * XD_LD + r4 + a] = -acc2[a][1]; }
-    }
-    __syncthreads();
+  //     first inside the two 64 x 64 diagonal blocks, then for the 64 x 64 block below them: four stages of 32^3
+  //     products on the tensor cores, 8 x 8 output fragments dealt round-robin to the warps.
+  auto blkA = [&](int i, int j) { return A + (32 * j) * PLD + 32 * i; };        // block (i, j) of the working matrix
+  auto put = [&](double* Cb, int ldc, int m0, int n0, double c0, double c1) {
+    *reinterpret_cast<double2*>(Cb + (n0 + lr) * ldc + m0 + 2 * lk) = make_double2(c0, c1);
+  };
+  // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1        (32 fragments, 4 per warp)
+  for (int t = warp; t < 32; t += 8) {
+    const int b = t >> 4, m0 = ((t >> 2) & 3) * 8, n0 = (t & 3) * 8;
+    double c0 = 0.0, c1 = 0.0;
+    frag_mm32(c0, c1, blkA(2 * b + 1, 2 * b), PLD, Xd + (2 * b) * XD_BLK, XD_LD, m0, n0, lk, lr);
+    put(Tm + b * XD_BLK, XD_LD, m0, n0, c0, c1);
   }
-  {
-    // stage 3: T2 = C A^-1 with C = blocks (2..3, 0..1):  T2_(i,0) = C_(i,0) X_00 + C_(i,1) X_10,  T2_(i,1) = C_(i,1) X_11.
-    // every thread takes one tile of a column-0 block (two products) and one of a column-1 block (one product)
-    const int ib = tid >> 7, tt = tid & 127, r4 = (tt & 7) * 4, c2 = (tt >> 3) * 2, i = 2 + ib;
-    double acc[4][2] = {};
-    blk32_fma(acc, blkA(i, 0), PB, Xd, XD_LD, r4, c2);
-    blk32_fma(acc, blkA(i, 1), PB, X10s, XD_LD, r4, c2);
-    double acc1[4][2] = {};
-    blk32_fma(acc1, blkA(i, 1), PB, Xd + XD_BLK, XD_LD, r4, c2);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      Tm[(2 * ib) * XD_BLK + c2 * XD_LD + r4 + a] = acc[a][0];
-      Tm[(2 * ib) * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc[a][1];
-      Tm[(2 * ib + 1) * XD_BLK + c2 * XD_LD + r4 + a] = acc1[a][0];
-      Tm[(2 * ib + 1) * XD_BLK + (c2 + 1) * XD_LD + r4 + a] = acc1[a][1];
-    }
-    __syncthreads();
-    // stage 4: X_C = -B^-1 T2:  X_(2,j) = -X_22 T2_(2,j),  X_(3,j) = -(X_32 T2_(2,j) + X_33 T2_(3,j)), j = 0, 1.
-    // thread -> column block j = tid >> 7: one tile of row block 2 (one product) and one of row block 3 (two products)
-    const int jb = tid >> 7;
-    double s2[4][2] = {};
-    blk32_fma(s2, Xd + 2 * XD_BLK, XD_LD, Tm + jb * XD_BLK, XD_LD, r4, c2);                 // T2_(2,jb) is Tm[jb]
-    double s3[4][2] = {};
-    blk32_fma(s3, blkA(3, 2), PB, Tm + jb * XD_BLK, XD_LD, r4, c2);
-    blk32_fma(s3, Xd + 3 * XD_BLK, XD_LD, Tm + (2 + jb) * XD_BLK, XD_LD, r4, c2);           // T2_(3,jb) is Tm[2 + jb]
-    double* d2 = blkA(2, jb) + c2 * PB + r4;
-    double* d3 = blkA(3, jb) + c2 * PB + r4;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      d2[a] = -s2[a][0]; d2[PB + a] = -s2[a][1];
-      d3[a] = -s3[a][0]; d3[PB + a] = -s3[a][1];
-    }
-    __syncthreads();
+  __syncthreads();
+  // stage 2: X_(2b+1, 2b) = -Xd_(2b+1) T_b
+  for (int t = warp; t < 32; t += 8) {
+    const int b = t >> 4, m0 = ((t >> 2) & 3) * 8, n0 = (t & 3) * 8;
+    double c0 = 0.0, c1 = 0.0;
+    frag_mm32(c0, c1, Xd + (2 * b + 1) * XD_BLK, XD_LD, Tm + b * XD_BLK, XD_LD, m0, n0, lk, lr);
+    put(blkA(2 * b + 1, 2 * b), PLD, m0, n0, -c0, -c1);
   }
+  __syncthreads();
+  // stage 3: T2 = C A^-1 with C = blocks (2..3, 0..1):  T2_(i,0) = C_(i,0) X_00 + C_(i,1) X_10,  T2_(i,1) = C_(i,1) X_11
+  //          (64 fragments; every warp takes two fragment positions in each of the four blocks -> equal work)
+  for (int t = warp; t < 64; t += 8) {
+    const int blk = (t >> 3) & 3, fpos = ((t >> 5) << 3) | (t & 7), ib = blk >> 1, jb = blk & 1, i = 2 + ib;
+    const int m0 = (fpos >> 2) * 8, n0 = (fpos & 3) * 8;
+    double c0 = 0.0, c1 = 0.0;
+    if (jb == 0) {
+      frag_mm32(c0, c1, blkA(i, 0), PLD, Xd, XD_LD, m0, n0, lk, lr);
+      frag_mm32(c0, c1, blkA(i, 1), PLD, blkA(1, 0), PLD, m0, n0, lk, lr);
+    } else {
+      frag_mm32(c0, c1, blkA(i, 1), PLD, Xd + XD_BLK, XD_LD, m0, n0, lk, lr);
+    }
+    put(Tm + (2 * ib + jb) * XD_BLK, XD_LD, m0, n0, c0, c1);
+  }
+  __syncthreads();
+  // stage 4: X_C = -B^-1 T2:  X_(2,j) = -X_22 T2_(2,j),  X_(3,j) = -(X_32 T2_(2,j) + X_33 T2_(3,j)), j = 0, 1
+  for (int t = warp; t < 64; t += 8) {
+    const int blk = (t >> 3) & 3, fpos = ((t >> 5) << 3) | (t & 7), ib = blk >> 1, jb = blk & 1;
+    const int m0 = (fpos >> 2) * 8, n0 = (fpos & 3) * 8;
+    double c0 = 0.0, c1 = 0.0;
+    if (ib == 0) {
+      frag_mm32(c0, c1, Xd + 2 * XD_BLK, XD_LD, Tm + jb * XD_BLK, XD_LD, m0, n0, lk, lr);
+    } else {
+      frag_mm32(c0, c1, blkA(3, 2), PLD, Tm + jb * XD_BLK, XD_LD, m0, n0, lk, lr);
+      frag_mm32(c0, c1, Xd + 3 * XD_BLK, XD_LD, Tm + (2 + jb) * XD_BLK, XD_LD, m0, n0, lk, lr);
+    }
+    put(blkA(2 + ib, jb), PLD, m0, n0, -c0, -c1);
+  }
+  __syncthreads();
   // (3) diagonal blocks from Xd, exact zeros above the diagonal (the panel solve sums over all 128 k)
   for (int id = tid; id < PB * PB; id += 256) {
     const int r = id & (PB - 1), cc = id >> 7;
-    if (r < cc) A[id] = 0.0;
-    else if ((r >> 5) == (cc >> 5)) A[id] = Xd[(r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31)];
+    if (r < cc) A[cc * PLD + r] = 0.0;
+    else if ((r >> 5) == (cc >> 5)) A[cc * PLD + r] = Xd[(r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31)];
   }
   fence_async_smem();
   __syncthreads();
   if (tid == 0) {
     double* dst = Linv + ((size_t)c * T + J) * PB * PB;
-    for (int col = 0; col < PB; ++col) bulk_s2g(dst + col * PB, A + col * PB, PB * 8);
+    for (int col = 0; col < PB; ++col) bulk_s2g(dst + col * PB, A + col * PLD, PB * 8);
     bulk_commit();
     bulk_wait0();
   }
