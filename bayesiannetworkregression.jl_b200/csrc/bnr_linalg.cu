@@ -177,23 +177,26 @@ __device__ __forceinline__ void syrk_diag_tile(const double* smem, unsigned long
 // the zero padding of n up to a multiple of 128 costs no tensor work.
 template <int MODE, int NF>
 __device__ __forceinline__ void syrk_strip_frags(const double* sj, const double* si, const double* ss, int k4,
-                                                 int warp, int lk, int lr,
+                                                 int f0, int f1, int lk, int lr,
                                                  double (&af)[2], double (&bf)[NF]) {
   const int kr = k4 * 4 + lk;
-  const double* rj = sj + kr * SY_LDS + warp * 16 + lr;
+  const double* rj = sj + kr * SY_LDS + lr;
   const double* ri = si + kr * SY_LDS + lr;
   if (MODE == 0) {
     const double sk = ss[kr];
-    af[0] = rj[0] * sk;
-    af[1] = rj[8] * sk;
+    af[0] = rj[f0 * 8] * sk;
+    af[1] = rj[f1 * 8] * sk;
   } else {
-    af[0] = rj[0];
-    af[1] = rj[8];
+    af[0] = rj[f0 * 8];
+    af[1] = rj[f1 * 8];
   }
 #pragma unroll
   for (int nf = 0; nf < NF; ++nf) bf[nf] = ri[nf * 8];
 }
 
+// MODE 2 (panel solve, the j operand is the lower-triangular inverse of the diagonal block): output column j' only
+// needs k <= j', so warp w takes the column fragments w and 15 - w (instead of 2w, 2w + 1) and stops feeding each of
+// them once k passes its last column: 2w + 2 and 32 - 2w k4-steps -- 34 of 64 for every warp, balanced.
 template <int MODE, int NF>
 __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned long long* full,
                                                 unsigned long long* empty, int nk, int warp, int lk, int lr, int lane,
@@ -203,25 +206,39 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < NF; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int f0 = (MODE == 2) ? warp : 2 * warp, f1 = (MODE == 2) ? 15 - warp : 2 * warp + 1;
+  const int lim0 = 2 * f0 + 2, lim1 = 2 * f1 + 2;       // MODE 2: k4-steps that can still reach the fragment
   double af[2][2], bf[2][NF];
   mbar_wait(&full[0], 0);
   const double* sj = smem;
-  syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, 0, warp, lk, lr, af[0], bf[0]);
+  syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, af[0], bf[0]);
   for (int kt = 0; kt < nk; ++kt) {
 #pragma unroll
     for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
       const int cur = k4 & 1, nxt = cur ^ 1;
       if (k4 + 1 < SY_BK / 4) {
-        syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, k4 + 1, warp, lk, lr, af[nxt], bf[nxt]);
+        syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, k4 + 1, f0, f1, lk, lr, af[nxt], bf[nxt]);
       } else if (kt + 1 < nk) {
         mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
         const double* nj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
-        syrk_strip_frags<MODE, NF>(nj, nj + SY_BK * SY_LDS, nj + 2 * SY_BK * SY_LDS, 0, warp, lk, lr, af[nxt], bf[nxt]);
+        syrk_strip_frags<MODE, NF>(nj, nj + SY_BK * SY_LDS, nj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, af[nxt], bf[nxt]);
       }
+      if (MODE == 2) {
+        const int k4g = kt * (SY_BK / 4) + k4;
+        if (k4g < lim0) {
 #pragma unroll
-      for (int nf = 0; nf < NF; ++nf) {
-        dmma884(acc[0][nf][0], acc[0][nf][1], af[cur][0], bf[cur][nf]);
-        dmma884(acc[1][nf][0], acc[1][nf][1], af[cur][1], bf[cur][nf]);
+          for (int nf = 0; nf < NF; ++nf) dmma884(acc[0][nf][0], acc[0][nf][1], af[cur][0], bf[cur][nf]);
+        }
+        if (k4g < lim1) {
+#pragma unroll
+          for (int nf = 0; nf < NF; ++nf) dmma884(acc[1][nf][0], acc[1][nf][1], af[cur][1], bf[cur][nf]);
+        }
+      } else {
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+          dmma884(acc[0][nf][0], acc[0][nf][1], af[cur][0], bf[cur][nf]);
+          dmma884(acc[1][nf][0], acc[1][nf][1], af[cur][1], bf[cur][nf]);
+        }
       }
     }
     __syncwarp();
@@ -230,7 +247,7 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
   }
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf) {
-    const int j = j0 + warp * 16 + mf * 8 + lr;
+    const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf) {
       const int i = i0 + nf * 8 + 2 * lk;
