@@ -278,17 +278,14 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
     }
     for (int g = 0; g < ng; ++g) {
       ChainGroup& G = h->groups[g];
-      // descending priorities break the symmetry between the groups: group 0's grids are dispatched first, so the
-      // groups drift half a sweep apart and one group's SYRK fills the SMs the other leaves idle in its panel phases
+      // main stream: greatest priority (latency-bound kernels); side stream: least (SYRK, bulk panel updates)
       int plo = 0, phi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&plo, &phi));       // plo = least, phi = greatest (numerically lower)
-      int prio = phi + g;
-      if (prio > plo) prio = plo;
-      if (getenv("BNR_NO_PRIO")) prio = plo;
+      const int prio = getenv("BNR_NO_PRIO") ? plo : phi;
       CK(cudaStreamCreateWithPriority(&G.stream, cudaStreamNonBlocking, prio));
       CK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
       if (use_side) {
-        CK(cudaStreamCreateWithPriority(&G.fj.side, cudaStreamNonBlocking, prio));
+        CK(cudaStreamCreateWithPriority(&G.fj.side, cudaStreamNonBlocking, plo));
         CK(cudaEventCreateWithFlags(&G.fj.fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&G.fj.join, cudaEventDisableTiming));
       }
@@ -347,8 +344,10 @@ static void refresh_xg(bnr_handle* h) {
   h->xg_valid = true;
 }
 
-// the gamma conditional: W, v, X v, rhs, G, Cholesky, solves, X' a4, gamma (and optionally S + lambda statistics)
-static void run_gamma(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s, int gig_flags) {
+// the gamma conditional: W, v, X v, rhs, G, Cholesky, solves, X' a4, gamma (and optionally S + lambda statistics).
+// syrk_forked: G = X D X' + I is already running on fj.side (enqueue_sweep forks it at the start of the sweep: it
+// depends on nothing but last sweep's S); wait for it just before the factorisation.
+static void run_gamma(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s, int gig_flags, bool syrk_forked = false) {
   if (e.d.gmode == BNR_GAMMA_QFORM) {
     // P = (X'X + D^-1)/tau2 = L L';  L w = X'(y - mu - X W)/tau2;  L' beta = w + z;  gamma = W + beta
     launch_edge_prep(e, 2, s);                        // W, v = z
@@ -364,19 +363,30 @@ static void run_gamma(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s,
   launch_edge_prep(e, 1, s);
   launch_x_times(e, 0, e.v, e.xv, ws, s);
   launch_rhs(e, s);
-  launch_syrk_G(e, s);
+  if (syrk_forked) cudaStreamWaitEvent(s, fj.join, 0);
+  else launch_syrk_G(e, s);
   launch_cholesky(e, e.rhs, fj, s);
   launch_chol_solve(e, e.rhs, nullptr, s);
   launch_x_times(e, 1, e.rhs, e.t, ws, s);
   launch_gamma_gig(e, gig_flags, s);
 }
 
-// one full sweep in gibbs_sample! order (src/gibbs.jl:663-677)
+// one full sweep in gibbs_sample! order (src/gibbs.jl:663-677).  The Gram SYRK (81 % of the sweep, pure throughput
+// work) goes to the low-priority side stream right away; the latency-bound kernels stay on the high-priority main
+// stream, so that they -- of this chain group and of the others -- get an SM as soon as any SYRK CTA retires instead
+// of queueing behind the SYRK's remaining CTAs.
 static void enqueue_sweep(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s) {
+  const bool fork_syrk = fj.side != nullptr && e.d.gmode == BNR_GAMMA_NFORM && !e.aux.G_copy;
+  if (fork_syrk) {
+    cudaEventRecord(fj.fork, s);
+    cudaStreamWaitEvent(fj.side, fj.fork, 0);
+    launch_syrk_G(e, fj.side);
+    cudaEventRecord(fj.join, fj.side);
+  }
   launch_tau2(e, s);
   launch_uxi(e, s);
   std::swap(e.u, e.u_alt);          // u now holds the new draw (pointer swap is baked per captured sweep)
-  run_gamma(e, ws, fj, s, 3);
+  run_gamma(e, ws, fj, s, 3, fork_syrk);
   launch_x_times(e, 0, e.gamma, e.xg, ws, s);
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
                        (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
@@ -432,7 +442,8 @@ static int build_graphs(bnr_handle* h) {
     enqueue_sweep(e, G.ws, G.fj, G.stream);
     enqueue_sweep(e, G.ws, G.fj, G.stream);
     CK(cudaStreamEndCapture(G.stream, &G.graph));
-    CK(cudaGraphInstantiate(&G.gexec, G.graph, 0));
+    // node priorities = priorities of the streams the kernels were captured from (main: greatest, side: least)
+    CK(cudaGraphInstantiate(&G.gexec, G.graph, getenv("BNR_NO_PRIO") ? 0 : cudaGraphInstantiateFlagUseNodePriority));
   }
   h->graph_kernels = g_launches - before;
   h->graphs_ready = true;
