@@ -128,6 +128,8 @@ static int row_offset(const Dims& d, int var) {
   return o[var];
 }
 
+static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, const double* y);
+
 extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y, bnr_handle** out) {
   if (!p || !X || !y || !out) return fail(BNR_EINVAL, "null argument");
   if (p->n < 1 || p->V < 2 || p->R < 1 || p->R > BNR_MAX_R || p->num_chains < 1)
@@ -144,6 +146,19 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
 
   bnr_handle* h = new bnr_handle();
   h->p = *p;
+  const int rc = create_impl(h, p, X, y);
+  if (rc != BNR_OK) {
+    const std::string msg = g_err;      // bnr_destroy must not clobber the reason
+    bnr_destroy(h);
+    g_err = msg;
+    return rc;
+  }
+  *out = h;
+  return BNR_OK;
+}
+
+// everything of bnr_create that can fail after the handle exists (the caller destroys the handle on failure)
+static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, const double* y) {
   if (h->p.gig_inject_len <= 0) h->p.gig_inject_len = 64;
   Dims& d = h->e.d;
   d.n = p->n; d.V = p->V; d.R = p->R; d.C = p->num_chains;
@@ -173,7 +188,6 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   // dynamic shared memory of the per-chain kernels grows with V*R
   const size_t need = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + 4 * (2 * d.V + 2 * d.R * d.R + 3 * d.R));
   if (need > 200 * 1024 || d.gdim > chol_max_dim()) {
-    delete h;
     return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R, or factored dimension > 4096)");
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -299,7 +313,6 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
   e.inj = nullptr; e.inj_stride = 0;
   memset(&e.aux, 0, sizeof(e.aux));
   CK(cudaStreamSynchronize(h->stream));
-  *out = h;
   return BNR_OK;
 }
 

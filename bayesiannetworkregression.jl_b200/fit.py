@@ -191,10 +191,11 @@ def _max(a):
 def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None, nburn=30000, nsamples=20000,
         mingen=0, maxgen=0, psrf_cutoff=1.01, x_transform=True, suppress_timer=False, num_chains=2, seed=None,
         purge_burn=None, filename="parameters.log", eta=None, zeta=None, iota=None, a_delta=None, b_delta=None,
-        nu=None, device=0, return_state="full", verbose=False):
+        nu=None, device=0, return_state="full", verbose=False, chain_offset=0):
     """Drop-in for `Fit!(X, y, R; ...)` (src/gibbs.jl:725-751).  Greek keyword names are accepted as in the
     reference; ASCII aliases (eta, zeta, iota, a_delta, b_delta, nu) are equivalent.  Extra, engine-only
-    keywords: device, return_state ("full" | "gamma_xi" | "none": how much of chain 1's table is copied back)."""
+    keywords: device, return_state ("full" | "gamma_xi" | "none": how much of chain 1's table is copied back),
+    chain_offset (global id of this GPU's first chain when several processes each fit a share of the chains)."""
     def pick(greek, ascii_, default):
         return default if (greek is None and ascii_ is None) else (greek if greek is not None else ascii_)
 
@@ -220,7 +221,8 @@ def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None
             fh.write("seed=%s" % seed)
     kw = dict(eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu,
               psrf_cutoff=psrf_cutoff, x_transform=x_transform, num_chains=num_chains, seed=seed,
-              purge_burn=purge_burn, device=device, return_state=return_state, verbose=verbose)
+              purge_burn=purge_burn, device=device, return_state=return_state, verbose=verbose,
+              chain_offset=chain_offset)
     if mingen > 0 and maxgen > 0:
         return generate_samples_dbl(X, y, R, mingen=mingen, maxgen=maxgen, **kw)
     return generate_samples(X, y, R, nburn=nburn, nsamp=nsamples, maxburn=nburn + nsamples, **kw)
@@ -249,7 +251,8 @@ def _normalise_purge(purge_burn, nburn):
 
 def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_delta=1.0, nu=10, nburn=30000,
                      nsamp=20000, maxburn=50000, psrf_cutoff=1.2, x_transform=True, num_chains=2, seed=None,
-                     purge_burn=None, device=0, return_state="full", verbose=False, engine_hook=None):
+                     purge_burn=None, device=0, return_state="full", verbose=False, engine_hook=None,
+                     chain_offset=0):
     """The "traditional" scheme (generate_samples!, src/gibbs.jl:897-1020)."""
     Xn, y = _prepare(X, y, R, nu, x_transform)
     total = nburn + nsamp
@@ -260,7 +263,8 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
     # (nburn >= nsamp, and the purge ring leaves room) their split-half moments are streamed on the device and only
     # chain 1 keeps a trace: memory is one chain's table instead of num_chains tables.
     streamed = nburn >= nsamp and nsamp >= 1 and (purge_burn is None or nsamp + purge_burn <= nburn)
-    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, trace_rows=tot_save,
+    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, chain_offset=chain_offset,
+                 trace_rows=tot_save,
                  trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=not streamed,
                  trace_gamma_xi_chains=1, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
     try:
@@ -300,7 +304,7 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
 
 def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_delta=1.0, nu=10, mingen=10000,
                          maxgen=100000, psrf_cutoff=1.01, x_transform=True, num_chains=2, seed=None,
-                         purge_burn=None, device=0, return_state="full", verbose=False):
+                         purge_burn=None, device=0, return_state="full", verbose=False, chain_offset=0):
     """The "doubling generation" scheme (generate_samples_dbl!, src/gibbs.jl:1051-1198)."""
     Xn, y = _prepare(X, y, R, nu, x_transform)
     nburn = _jround(mingen / 2)
@@ -312,7 +316,8 @@ def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, 
     rounds = max(0, math.ceil((maxgen - total) / max(mingen, 1)))
     capacity = max(tot_save, nsamp + (rounds + 1) * halfburn + halfburn)
     seed = random.randint(1, 55555) if seed is None else seed
-    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, trace_rows=capacity,
+    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, chain_offset=chain_offset,
+                 trace_rows=capacity,
                  trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=True,
                  eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
     try:

@@ -288,23 +288,23 @@ def main():
     eng.close()
 
     # ---------------- end to end through the public API with HOST buffers: `e2e` ----------------
+    # The call a user makes: Fit(X, y, R; nburn, nsamples, num_chains, seed) -> Results, then Summary(Results).
+    # Inside the timed region: cudaMalloc, H2D of X and y, prior init, K sweeps of every chain, streamed R-hat,
+    # Summary reduced on the device, D2H of chain 1's gamma / xi table, the R-hat vectors and the Summary statistics.
+    nsamp_e = max(4, K // 2)
+    nburn_e = K + 1 - nsamp_e                      # nburn + nsamples rows = prior row + K sweeps
     barrier()
     t0 = time.perf_counter()
-    e2 = bnr.Engine(X, y, R, num_chains=chains, seed=7, chain_offset=rank * chains, device=local_rank,
-                    trace_rows=K + 1, trace_full_chains=0, trace_gamma_xi_all=True, chain_groups=args.chain_groups,
-                    gamma_mode=args.gamma_mode)                                           # H2D of X, y
-    e2.init_state()
-    e2.set_moment_window(1, K)
-    e2.run(K)
-    g0 = e2.get_trace(0, "gamma", 1, K + 1)                                               # D2H: chain 1's gamma / xi
-    x0 = e2.get_trace(0, "xi", 1, K + 1)
-    r2 = e2.rhat()
-    e2.close()
+    res = bnr.Fit(X, y, R, nburn=nburn_e, nsamples=nsamp_e, num_chains=chains, seed=7, x_transform=False,
+                  filename=None, psrf_cutoff=float("inf"), device=local_rank, chain_offset=rank * chains,
+                  return_state="gamma_xi")
+    summ = bnr.Summary(res)
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = world * chains * K / e2e_s
     h2d = (X.nbytes + y.nbytes) / K
-    d2h = (g0.nbytes + x0.nbytes + r2[0].nbytes + r2[1].nbytes) / K
+    d2h = (res.state["gamma"].nbytes + res.state["xi"].nbytes + 8 * (V + q) + 8 * (3 * q + V)) / K
+    assert len(summ.edge_coef["estimate"]) == q and res.extra["tot_generated"] == K + 1
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -324,8 +324,8 @@ def main():
             "config": workload_config(args, dims, chains),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "chain-iterations/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "includes": "cudaMalloc + H2D of X,y + prior init + K sweeps + D2H of "
-                    "chain-1 gamma/xi traces and R-hat"},
+                    "d2h_bytes_per_step": d2h, "includes": "Fit(X, y, R; ...) + Summary through the public API: cudaMalloc, "
+                    "H2D of X,y, prior init, K sweeps, streamed R-hat, device Summary, D2H of chain-1 gamma/xi table"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom_kernel,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
