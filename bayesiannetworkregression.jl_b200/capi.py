@@ -41,6 +41,8 @@ PROTOTYPES = {
     "bnr_default_params": (None, [C.POINTER(Params)]),
     "bnr_create": (C.c_int, [C.POINTER(Params), _DP, _DP, C.POINTER(_H)]),
     "bnr_destroy": (C.c_int, [_H]),
+    "bnr_set_cache_limit": (C.c_int, [C.c_int64]),
+    "bnr_trim_cache": (C.c_int, []),
     "bnr_init_state": (C.c_int, [_H]),
     "bnr_run": (C.c_int, [_H, C.c_int64]),
     "bnr_sync": (C.c_int, [_H]),

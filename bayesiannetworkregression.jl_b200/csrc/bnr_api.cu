@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -50,6 +51,45 @@ struct ChainGroup {
 };
 constexpr int MAX_GROUPS = 4;
 
+// ---------------------------------------------------------------------------------------------------------
+// Device-memory cache.  Releasing gigabytes with cudaFree costs 30 - 300 ms (occasionally seconds) and synchronises
+// the device; a handle's buffers therefore go back to a process-wide cache keyed by (device, size) when the handle
+// is destroyed and are handed to the next handle that asks for the same size (the common case: Fit called again on
+// the same problem, or the PSRF loop of a wrapper re-creating engines).  bnr_set_cache_limit bounds what is kept
+// (default 4 GiB per process), bnr_trim_cache releases it.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct CacheBlock { void* p; size_t bytes; int device; };
+std::mutex g_cache_mu;
+std::vector<CacheBlock> g_cache;
+size_t g_cache_bytes = 0;
+size_t g_cache_limit = (size_t)4 << 30;
+
+void* cache_take(int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (size_t i = 0; i < g_cache.size(); ++i)
+    if (g_cache[i].device == device && g_cache[i].bytes == bytes) {
+      void* p = g_cache[i].p;
+      g_cache_bytes -= bytes;
+      g_cache[i] = g_cache.back();
+      g_cache.pop_back();
+      return p;
+    }
+  return nullptr;
+}
+void cache_give(int device, void* p, size_t bytes) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache_bytes + bytes <= g_cache_limit) {
+      g_cache.push_back({p, bytes, device});
+      g_cache_bytes += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+}  // namespace
+
 struct bnr_handle {
   bnr_params p;
   Engine e;
@@ -60,7 +100,7 @@ struct bnr_handle {
   cudaEvent_t ev_fork = nullptr;
   ForkJoin fj;                   // side stream for eager sweeps on the whole chain set
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;   // device buffers (pointer, bytes): returned to the cache on destroy
   double* ws = nullptr;          // split-K workspace
   double* d_inj = nullptr;       // injected variates
   long long inj_len = 0;
@@ -82,12 +122,21 @@ struct bnr_handle {
   size_t acov_cap = 0;
 };
 
+static int raw_alloc(bnr_handle* h, void** out, size_t bytes) {
+  void* p = cache_take(h->p.device, bytes);
+  if (!p) CK(cudaMalloc(&p, bytes));
+  h->allocs.push_back({p, bytes});
+  *out = p;
+  return 0;
+}
+
 template <typename T>
 static int dalloc(bnr_handle* h, T** ptr, size_t count, bool zero = true) {
   void* p = nullptr;
-  CK(cudaMalloc(&p, count * sizeof(T) + 16));
-  if (zero) CK(cudaMemsetAsync(p, 0, count * sizeof(T) + 16, h->stream));
-  h->allocs.push_back(p);
+  const size_t bytes = count * sizeof(T) + 16;
+  int r = raw_alloc(h, &p, bytes);
+  if (r) return r;
+  if (zero) CK(cudaMemsetAsync(p, 0, bytes, h->stream));
   *ptr = (T*)p;
   return 0;
 }
@@ -318,6 +367,27 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
 
 static void drop_graph(bnr_handle* h);
 
+extern "C" int bnr_trim_cache(void) {
+  std::vector<CacheBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    blocks.swap(g_cache);
+    g_cache_bytes = 0;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& b : blocks) { cudaSetDevice(b.device); cudaFree(b.p); }
+  cudaSetDevice(cur);
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_cache_limit(int64_t bytes) {
+  if (bytes < 0) return fail(BNR_EINVAL, "negative limit");
+  { std::lock_guard<std::mutex> lk(g_cache_mu); g_cache_limit = (size_t)bytes; }
+  if (bytes == 0) return bnr_trim_cache();
+  return BNR_OK;
+}
+
 extern "C" int bnr_destroy(bnr_handle* h) {
   if (!h) return BNR_OK;
   cudaSetDevice(h->p.device);
@@ -334,7 +404,7 @@ extern "C" int bnr_destroy(bnr_handle* h) {
   if (h->fj.fork) cudaEventDestroy(h->fj.fork);
   if (h->fj.join) cudaEventDestroy(h->fj.join);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  for (void* p : h->allocs) cudaFree(p);
+  for (auto& a : h->allocs) cache_give(h->p.device, a.first, a.second);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -812,10 +882,10 @@ extern "C" int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_c
   if (!inj) { h->e.inj = nullptr; h->e.inj_stride = 0; return BNR_OK; }
   const size_t total = (size_t)per_chain * h->e.d.C;
   if ((long long)total > h->inj_len) {
-    double* p = nullptr;
-    CK(cudaMalloc((void**)&p, total * sizeof(double)));
-    h->allocs.push_back(p);
-    h->d_inj = p;
+    void* p = nullptr;
+    int r = raw_alloc(h, &p, total * sizeof(double));
+    if (r) return r;
+    h->d_inj = (double*)p;
     h->inj_len = (long long)total;
   }
   CK(cudaMemcpy(h->d_inj, inj, total * sizeof(double), cudaMemcpyHostToDevice));
@@ -1037,10 +1107,10 @@ extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrow
   const int P = d.V + d.q;
   const size_t need = (size_t)(max_lag + 1) * P;
   if (need > h->acov_cap) {
-    double* pnew = nullptr;
-    CK(cudaMalloc((void**)&pnew, need * sizeof(double)));
-    h->allocs.push_back(pnew);
-    h->d_acov = pnew;
+    void* pnew = nullptr;
+    int r = raw_alloc(h, &pnew, need * sizeof(double));
+    if (r) return r;
+    h->d_acov = (double*)pnew;
     h->acov_cap = need;
   }
   if (!h->d_cmean) DA(h->d_cmean, (size_t)d.C * P);

@@ -144,6 +144,11 @@ void bnr_default_params(bnr_params* p);
 /* X: n x q column-major host array, y: n.  Copies both to the device (padded, L2-friendly). */
 int bnr_create(const bnr_params* p, const double* X, const double* y, bnr_handle** out);
 int bnr_destroy(bnr_handle* h);
+/* bnr_destroy returns the handle's device buffers to a process-wide cache (cudaFree of gigabytes is slow and
+ * synchronises the device); the next bnr_create reuses buffers of equal size.  bnr_set_cache_limit bounds the
+ * cached bytes (default 4 GiB; 0 disables caching and trims), bnr_trim_cache releases everything cached. */
+int bnr_set_cache_limit(int64_t bytes);
+int bnr_trim_cache(void);
 
 /* Row 1 of every chain from the priors (initialize_variables!), iteration counter := 0. */
 int bnr_init_state(bnr_handle* h);
