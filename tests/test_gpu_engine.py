@@ -508,3 +508,31 @@ def test_config2_qform_matches_nform_and_oracle_chain():
                    for s_ in (1, 2)], axis=0)
     assert np.abs(prob["auto"] - prob["nform"]).max() < 0.03
     assert np.abs(prob["auto"] - ora).max() < 0.07
+
+
+def test_device_memory_cache_is_transparent(bnr):
+    """Handles created from recycled device buffers (the process-wide cache behind bnr_destroy) behave exactly like
+    fresh ones; the cache can be switched off and trimmed."""
+    X, y = _toy(5, V=8, R=3, n=40)
+    L = bnr.lib()
+
+    def run():
+        with bnr.Engine(X, y, 3, num_chains=3, seed=21, trace_rows=8) as eng:
+            eng.init_state()
+            eng.run(7)
+            return eng.get_state_dict(2), eng.get_trace(0, "gamma", 0, 8).copy()
+
+    try:
+        assert L.bnr_set_cache_limit(0) == 0            # no caching: every buffer is cudaMalloc'ed / cudaFree'd
+        a = run()
+        assert L.bnr_set_cache_limit(4 << 30) == 0
+        b = run()                                      # fills the cache on destroy
+        c = run()                                      # served from the cache (stale contents in non-zeroed buffers)
+        assert L.bnr_trim_cache() == 0
+        d = run()
+    finally:
+        L.bnr_set_cache_limit(4 << 30)
+    for other in (b, c, d):
+        for k in a[0]:
+            np.testing.assert_array_equal(np.asarray(a[0][k]), np.asarray(other[0][k]), err_msg=k)
+        np.testing.assert_array_equal(a[1], other[1])
