@@ -140,6 +140,17 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def _finite(o):
+    """JSON has no NaN / Infinity: non-finite floats become null."""
+    if isinstance(o, float):
+        return o if math.isfinite(o) else None
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    return o
+
+
 def workload_config(args, dims, chains):
     return {"workload": "BASELINE config 3-style synthetic network regression" if args.config == "c3" else args.config,
             "name": args.config, "V": dims["V"], "q": dims["q"], "n": dims["n"], "R": dims["R"],
@@ -227,7 +238,9 @@ def main():
     value = world * chains * K / (total_ms * 1e-3)
 
     # R-hat over all chains of all ranks: NCCL all-gather of split-half moments, reduced identically on every rank
-    if world > 1:
+    if K // 2 < 2:
+        rx, rg = np.full(V, np.nan), np.full(q, np.nan)        # too few timed draws for a split R-hat
+    elif world > 1:
         ptr, cnt = eng.moments_device()
         mine = torch.empty(cnt, dtype=torch.float64, device=dev)
         eng.export_moments(mine.data_ptr())
@@ -243,9 +256,14 @@ def main():
     # lag sums + Geyer's initial monotone sequence); across GPUs the per-rank autocovariance sums and chain means are
     # all-gathered over NCCL and reduced identically on every rank
     max_lag = min(255, K - 1)
-    eng.ess_accumulate(Wm + 1, K, max_lag)
-    (pa, na), (pm, nm), lag = eng.ess_device()
-    if world > 1:
+    ess_x = ess_g = None
+    lag = 0
+    if K >= 4:
+        eng.ess_accumulate(Wm + 1, K, max_lag)
+        (pa, na), (pm, nm), lag = eng.ess_device()
+    if K < 4:
+        ess_g = np.full(q, np.nan)
+    elif world > 1:
         a_mine = torch.empty(na, dtype=torch.float64, device=dev)
         m_mine = torch.empty(nm, dtype=torch.float64, device=dev)
         eng.export_ess(a_mine.data_ptr(), m_mine.data_ptr())
@@ -257,8 +275,8 @@ def main():
         ess_x, ess_g = eng.ess_from_stats(a_all.data_ptr(), world, m_all.data_ptr(), chains * world, K, lag)
     else:
         ess_x, ess_g = eng.ess_from_stats(pa, 1, pm, chains, K, lag)
-    ess_med = float(np.nanmedian(ess_g))
-    ess_min = float(np.nanmin(ess_g))
+    ess_med = float(np.nanmedian(ess_g)) if np.isfinite(ess_g).any() else float("nan")
+    ess_min = float(np.nanmin(ess_g)) if np.isfinite(ess_g).any() else float("nan")
 
     # ---------------- per-phase CUDA-event profile of eager sweeps (roofline numerator) ----------------
     phases = {}
@@ -291,20 +309,20 @@ def main():
     # The call a user makes: Fit(X, y, R; nburn, nsamples, num_chains, seed) -> Results, then Summary(Results).
     # Inside the timed region: handle creation, H2D of X and y, prior init, K sweeps of every chain, streamed R-hat,
     # Summary reduced on the device, D2H of chain 1's gamma / xi table, the R-hat vectors and the Summary statistics.
-    nsamp_e = max(4, K // 2)
+    nsamp_e = min(max(2, K // 2), K)
     nburn_e = K + 1 - nsamp_e                      # nburn + nsamples rows = prior row + K sweeps
     barrier()
     t0 = time.perf_counter()
     res = bnr.Fit(X, y, R, nburn=nburn_e, nsamples=nsamp_e, num_chains=chains, seed=7, x_transform=False,
                   filename=None, psrf_cutoff=float("inf"), device=local_rank, chain_offset=rank * chains,
                   return_state="gamma_xi")
-    summ = bnr.Summary(res)
+    summ = bnr.Summary(res) if nsamp_e >= 40 else None     # the reference's Summary needs >= 20 draws per tail index
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = world * chains * K / e2e_s
     h2d = (X.nbytes + y.nbytes) / K
     d2h = (res.state["gamma"].nbytes + res.state["xi"].nbytes + 8 * (V + q) + 8 * (3 * q + V)) / K
-    assert len(summ.edge_coef["estimate"]) == q and res.extra["tot_generated"] == K + 1
+    assert (summ is None or len(summ.edge_coef["estimate"]) == q) and res.extra["tot_generated"] == K + 1
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -342,11 +360,11 @@ def main():
             "algorithmic_tflops": value * algo_flops / 1e12,
             "phases_ms": phases,
             "wall_ms_per_step": wall_ms / K,
-            "rhat": {"max_gamma": float(np.nanmax(rg)), "max_xi": float(np.nanmax(rx[np.isfinite(rx)])) if np.isfinite(rx).any() else None,
+            "rhat": {"max_gamma": float(np.nanmax(rg)) if np.isfinite(rg).any() else None, "max_xi": float(np.nanmax(rx[np.isfinite(rx)])) if np.isfinite(rx).any() else None,
                      "chains": chains * world},
             "status_or": int(np.bitwise_or.reduce(status)),
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_finite(line)), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
