@@ -184,3 +184,27 @@ def test_input_formats_roundtrip(bnr, tmp_path, golden):
         bad = tmp_path / "bad.csv"
         np.savetxt(bad, np.zeros((3, 8)), delimiter=",", header="a,b,c,d,e,f,g,h", comments="")
         bnr.read_matrix_networks(str(bad))
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "bayesiannetworkregression.jl_b200")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", pkg, "-lbnr",
+                    "-Wl,-rpath," + pkg, "-lm"], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_links(bnr, tmp_path):
+    """include/bnr.h compiles as strict C99 and a plain-C client links against libbnr.so: the boundary a Julia ccall /
+    cgo / JNI binding sees.  Without a GPU the client must stop with BNR_ENODEV (exit code 3), never fall back."""
+    import subprocess
+    import torch
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr

@@ -536,3 +536,13 @@ def test_device_memory_cache_is_transparent(bnr):
         for k in a[0]:
             np.testing.assert_array_equal(np.asarray(a[0][k]), np.asarray(other[0][k]), err_msg=k)
         np.testing.assert_array_equal(a[1], other[1])
+
+
+def test_plain_c_client_runs_a_fit(bnr, tmp_path):
+    """The plain-C client of include/bnr.h (tests/c/abi_smoke.c) creates a handle, runs sweeps, reads R-hat and a trace."""
+    import subprocess
+    from test_abi_and_host import _build_c_client
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe, "60", "10", "3", "6", "80"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sweeps 80" in r.stdout
