@@ -140,15 +140,48 @@ def _run_rows(eng, first_index, nburn, total, purge_burn):
         eng.run(seg_len)
 
 
+def _dist_world():
+    """(rank, world) of an initialised torch.distributed process group, else (0, 1).  One process per GPU: every rank
+    calls Fit with its own share of the chains (the reference spreads chains over Distributed.jl workers,
+    src/gibbs.jl:946-948)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
 def _psrf(eng, nb, nsamp, streamed=False):
     """return_psrf_VOI (src/gibbs.jl:771-789): R-hat over table rows nb+1 .. nb+nsamp of every chain.
     streamed: the split-half moments of exactly those draws were accumulated while the chains ran
-    (bnr_set_moment_window), so no chain but the first needs a trace."""
+    (bnr_set_moment_window), so no chain but the first needs a trace.
+    In a torch.distributed job the per-rank moments ([chain][half][param][mean, M2], 32 (V+q) bytes per chain -- the
+    only data that crosses NVLink) are all-gathered and every rank reduces them in the same order, so all ranks take
+    the same PSRF decisions."""
     if nsamp // 2 < 2:
         return np.full(eng.V, np.nan), np.full(eng.q, np.nan)
     if not streamed:
         eng.moments_from_trace(nb, nsamp)
-    return eng.rhat()
+    rank, world = _dist_world()
+    if world == 1:
+        return eng.rhat()
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", eng.device)
+    _, cnt = eng.moments_device()
+    mine = torch.empty(cnt, dtype=torch.float64, device=dev)
+    eng.export_moments(mine.data_ptr())
+    if dist.get_backend() == "nccl":
+        allm = torch.empty(cnt * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allm, mine)
+    else:                                   # gloo (tests, CPU-side rendezvous): gather on the host
+        host = torch.empty(cnt * world, dtype=torch.float64)
+        dist.all_gather_into_tensor(host, mine.cpu())
+        allm = host.to(dev)
+    torch.cuda.synchronize(dev)
+    return eng.rhat_from_moments(allm.data_ptr(), eng.C * world, eng.moment_half_len())
 
 
 def _stream_last(eng, new_sweeps, nsamp):
@@ -195,7 +228,9 @@ def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None
     """Drop-in for `Fit!(X, y, R; ...)` (src/gibbs.jl:725-751).  Greek keyword names are accepted as in the
     reference; ASCII aliases (eta, zeta, iota, a_delta, b_delta, nu) are equivalent.  Extra, engine-only
     keywords: device, return_state ("full" | "gamma_xi" | "none": how much of chain 1's table is copied back),
-    chain_offset (global id of this GPU's first chain when several processes each fit a share of the chains)."""
+    chain_offset (global id of this GPU's first chain when several processes each fit a share of the chains;
+    default rank * num_chains inside a torch.distributed job, where num_chains is the count PER RANK and the R-hat
+    tables cover the chains of all ranks)."""
     def pick(greek, ascii_, default):
         return default if (greek is None and ascii_ is None) else (greek if greek is not None else ascii_)
 
@@ -207,6 +242,12 @@ def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None
     nu = pick(ν, nu, 10)
     if seed is None:
         seed = random.randint(1, 55555)
+    rank, world = _dist_world()
+    if world > 1:
+        if chain_offset == 0:
+            chain_offset = rank * num_chains
+        if rank != 0:
+            filename = None                  # one parameters.log per job
     if filename:
         with open(filename, "w") as fh:
             fh.write("BayesianNetworkRegression.jl Fit! function\n")
