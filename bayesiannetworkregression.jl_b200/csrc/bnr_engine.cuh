@@ -9,7 +9,6 @@ namespace bnr {
 constexpr int MAX_R = 16;
 constexpr int TILE_N = 128;   // n is padded to a multiple of this (SYRK / Cholesky tiles)
 constexpr int TILE_K = 16;    // q is padded to a multiple of this (SYRK k-step)
-constexpr int CHOL_NB = 64;   // Cholesky panel width
 constexpr int PART_BLOCK = 256;  // threads per block of the edge kernels (partials granularity)
 
 struct Dims {

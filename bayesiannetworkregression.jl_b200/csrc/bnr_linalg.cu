@@ -1,5 +1,5 @@
 // Dense FP64 linear algebra of the gamma draw (update_gamma!, src/gibbs.jl:420-438), batched over chains:
-//   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, cp.async 3-stage pipeline
+//   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, TMA bulk-copy ring + mbarriers
 //   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_augment / k_chol_update (DMMA) / k_potf2_inv /
 //                                        k_trsm_dmma (DMMA); the forward solve rides along as a bordering row
 //   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
@@ -16,10 +16,6 @@ namespace bnr {
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -59,6 +55,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // SYRK on FP64 tensor cores.
 //   MODE 0:  C_c[i][j] = sum_k A[i][k] s_c[k] A[j][k] + (i==j)      A = X (shared by all chains), K = qp
 //   MODE 1:  C_c[i][j] -= sum_{k < nk*16} L_c[i][k] L_c[j][k]        left-looking Cholesky update of block column J
+//   MODE 2:  C_c[i][j]  = sum_{k < 128} C_c[i][k] Linv_c[j][k]       panel solve with the inverted diagonal block
 // The operand is "k-major": element (row, k) at A[row + ld*k] (rows contiguous) - exactly how X (column-major
 // n x q) and a column panel of the column-major G are stored, so a 128-row x 16-k tile is sixteen contiguous
 // 1 KB rows.  A dedicated producer warp streams them into a 4-stage shared-memory ring with TMA-engine bulk
@@ -527,7 +524,7 @@ __device__ __forceinline__ void frag_mm32(double& c0, double& c1, const double* 
 constexpr int PLD = 132;           // column stride of the 128 x 128 working block (== 4 mod 16: conflict-free fragments)
 constexpr int XD_LD = 36;          // column stride of the 32 x 32 scratch blocks (== 4 mod 16)
 constexpr int XD_BLK = 32 * XD_LD;
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 9 * XD_BLK + PB + 64) + 16;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB + 64) + 16;
 
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_t chain_stride, int N, int J,
                                                    double* __restrict__ Linv, int T, int* status) {
@@ -535,8 +532,7 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   double* A = sm;                          // column-major 128 x 128 working block: A[col * PLD + row]
   double* Xd = sm + PB * PLD;              // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
   double* Tm = Xd + 4 * XD_BLK;            // [4] intermediate products of the inverse
-  double* X10s = Tm + 4 * XD_BLK;          // [1] spare block
-  double* dall = X10s + XD_BLK;            // [128] reciprocal diagonal of L
+  double* dall = Tm + 4 * XD_BLK;          // [128] reciprocal diagonal of L
   double* Lcol = dall + PB;                // [2][32] current column of the 32 x 32 factorisation (double-buffered)
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
