@@ -52,6 +52,8 @@ PROTOTYPES = {
     "bnr_get_trace_row": (C.c_int, [_H, _I64P]),
     "bnr_copy_trace_rows": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
     "bnr_set_moment_window": (C.c_int, [_H, C.c_int64, C.c_int64]),
+    "bnr_set_moment_blocks": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int32]),
+    "bnr_moments_from_blocks": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "bnr_moments_device": (C.c_int, [_H, C.POINTER(C.c_void_p), _I64P]),
     "bnr_rhat_from_moments": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _DP, _DP]),
     "bnr_moments_from_trace": (C.c_int, [_H, C.c_int64, C.c_int64]),

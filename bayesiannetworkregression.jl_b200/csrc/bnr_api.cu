@@ -106,7 +106,9 @@ struct bnr_handle {
   long long inj_len = 0;
   bool aux_on = false;
   Aux aux_saved = {};
- long long mom_half = 0;        // draws per split chain behind the current moments buffer
+  long long win[5] = {0, 0, 0, 1, 0};   // host copy of the device window record (bnr_set_moment_window / _blocks)
+  long long blk_len = 0;
+  long long mom_half = 0;        // draws per split chain behind the current moments buffer
   long long launches = 0;        // kernels launched by bnr_run so far (graph replays included)
   long long graph_kernels = 0;   // kernels inside the captured two-sweep graphs (all groups)
   bool xg_valid = false;         // e.xg == X * gamma for the current state
@@ -305,7 +307,8 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   DA(e.status, C);
   DA(e.iter, 1); DA(e.trace_row, 1);
   DA(e.moments, C * 2 * (d.V + d.q) * 2);
-  DA(e.mom_window, 2);
+  DA(e.mom_window, 5);
+  e.bmom = nullptr; e.bmom_nb = 0;
   DA(h->ws, x_times_workspace_doubles(d));
   DA(h->d_rhat, (size_t)(d.V + d.q));
   e.trace_full_chains = p->trace_rows > 0 ? (p->trace_full_chains < d.C ? p->trace_full_chains : d.C) : 0;
@@ -354,7 +357,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
       }
       DA(G.ws, x_times_workspace_doubles(d));
       DA(G.counters, 2);
-      DA(G.mom_window, 2);
+      DA(G.mom_window, 5);
     }
   }
   h->tmp_doubles = (size_t)1 << 22;
@@ -493,6 +496,7 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   v.G += c * d.gdim * d.gdim; if (v.syrk_ws) v.syrk_ws += c * (size_t)v.syrk_ws_cap * d.gdim * d.gdim; v.Linv += c * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N;
   v.partials += c * d.nparts * (2 * MAX_R + 1);
   v.moments += c * 2 * (d.V + d.q) * 2;
+  if (v.bmom) v.bmom += c * (size_t)v.bmom_nb * (d.V + d.q) * 2;
   int tgc = h->e.trace_gx_chains - c0;
   tgc = tgc < 0 ? 0 : (tgc > Cg ? Cg : tgc);
   v.trace_gx_chains = tgc;
@@ -661,14 +665,71 @@ extern "C" int bnr_copy_trace_rows(bnr_handle* h, int64_t dst, int64_t src, int6
   return BNR_OK;
 }
 
+// device copy of the 5-entry window record (split-half window + block-moment configuration) for the handle and groups
+static int push_windows(bnr_handle* h) {
+  CK(cudaMemcpyAsync(h->e.mom_window, h->win, sizeof(h->win), cudaMemcpyHostToDevice, h->stream));
+  for (int g = 0; g < h->n_groups; ++g)
+    CK(cudaMemcpyAsync(h->groups[g].mom_window, h->win, sizeof(h->win), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return BNR_OK;
+}
+
 extern "C" int bnr_set_moment_window(bnr_handle* h, int64_t first, int64_t len) {
   if (!h || len < 0) return fail(BNR_EINVAL, "bad arguments");
-  long long w[2] = {first, len};
-  CK(cudaMemcpyAsync(h->e.mom_window, w, sizeof(w), cudaMemcpyHostToDevice, h->stream));
-  for (int g = 0; g < h->n_groups; ++g)
-    CK(cudaMemcpyAsync(h->groups[g].mom_window, w, sizeof(w), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  h->win[0] = first; h->win[1] = len;
+  int r = push_windows(h);
+  if (r) return r;
   h->mom_half = len / 2;
+  return BNR_OK;
+}
+
+extern "C" int bnr_set_moment_blocks(bnr_handle* h, int64_t first_sweep, int64_t block_len, int32_t nblocks) {
+  if (!h || nblocks < 0 || (nblocks > 0 && block_len < 1)) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
+  const Dims& d = h->e.d;
+  if (nblocks > h->e.bmom_nb) {
+    CK(cudaStreamSynchronize(h->stream));
+    drop_graph(h);                       // the group views carry the buffer pointer and its block capacity
+    void* p = nullptr;
+    int r = raw_alloc(h, &p, sizeof(double) * (size_t)d.C * nblocks * (d.V + d.q) * 2);
+    if (r) return r;
+    h->e.bmom = (double*)p;
+    h->e.bmom_nb = nblocks;
+  }
+  h->win[2] = first_sweep; h->win[3] = block_len > 0 ? block_len : 1; h->win[4] = nblocks;
+  h->blk_len = block_len;
+  return push_windows(h);
+}
+
+// merge blocks [first_block, first_block + nblocks) (nblocks even) into the split-half moments: Chan's pairwise update
+// applied block after block in a fixed order.  grid = (ceil(P/128), C, 2)
+__global__ void k_merge_blocks(const double* __restrict__ bmom, int nb_cap, int nparam, int first_block, int per_half,
+                               long long blen, double* __restrict__ mom) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nparam) return;
+  const int c = blockIdx.y, half = blockIdx.z;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int b = 0; b < per_half; ++b) {
+    const double* m = bmom + (((size_t)c * nb_cap + first_block + half * per_half + b) * nparam + p) * 2;
+    const double nb_ = (double)blen, delta = m[0] - mean, tot = n + nb_;
+    mean += delta * nb_ / tot;
+    m2 += m[1] + delta * delta * n * nb_ / tot;
+    n = tot;
+  }
+  double* o = mom + (((size_t)c * 2 + half) * nparam + p) * 2;
+  o[0] = mean; o[1] = m2;
+}
+
+extern "C" int bnr_moments_from_blocks(bnr_handle* h, int32_t first_block, int32_t nblocks) {
+  if (!h || first_block < 0 || nblocks < 2 || (nblocks & 1)) return fail(BNR_EINVAL, "need an even number of blocks >= 2");
+  if (!h->e.bmom || first_block + nblocks > (int)h->win[4]) return fail(BNR_ESTATE, "blocks not configured (bnr_set_moment_blocks)");
+  const Dims& d = h->e.d;
+  const int np_ = d.V + d.q;
+  dim3 grid((np_ + 127) / 128, d.C, 2);
+  k_merge_blocks<<<grid, 128, 0, h->stream>>>(h->e.bmom, h->e.bmom_nb, np_, first_block, nblocks / 2, h->blk_len, h->e.moments);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->mom_half = (long long)(nblocks / 2) * h->blk_len;
   return BNR_OK;
 }
 

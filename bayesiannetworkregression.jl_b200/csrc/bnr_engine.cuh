@@ -111,7 +111,9 @@ struct Engine {
   long long* trace_row;   // device scalar: next trace row
   // moments [C][2][V+q][2] and window
   double* moments;
-  long long* mom_window;  // device [2]: first sweep, len
+  long long* mom_window;  // device [5]: split-half window (first sweep, len), block moments (first sweep, block len, blocks)
+  double* bmom;           // [C][bmom_nb][V+q][2] per-block (mean, M2): mergeable R-hat windows (doubling scheme)
+  int bmom_nb;
   // traces
   int trace_full_chains; int trace_gx_chains; long long trace_rows;   // leading chains with full / (xi, gamma) rows
   double* tr_full;  // [trace_full_chains][rows][rowlen_full]

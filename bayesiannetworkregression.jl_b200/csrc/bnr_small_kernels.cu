@@ -682,6 +682,21 @@ __global__ void __launch_bounds__(256) k_record(Engine e, int sweep_done /* 1: s
         m[0] = mean; m[1] = m2;
       }
     }
+    // block moments: sweep s belongs to block (s - first) / block_len; blocks are merged later into any window made
+    // of whole blocks (bnr_moments_from_blocks) -- the doubling scheme's growing window without all-chain traces
+    const long long bfirst = e.mom_window[2], blen = e.mom_window[3], bcnt = e.mom_window[4];
+    if (e.bmom && bcnt > 0 && sweep >= bfirst) {
+      const long long b = (sweep - bfirst) / blen;
+      if (b < bcnt && b < e.bmom_nb) {
+        const long long cnt = (sweep - bfirst) % blen + 1;
+        double* m = e.bmom + (((size_t)c * e.bmom_nb + b) * np_ + p) * 2;
+        double mean = (cnt == 1) ? 0.0 : m[0], m2 = (cnt == 1) ? 0.0 : m[1];
+        const double dl = x - mean;
+        mean += dl / (double)cnt;
+        m2 += dl * (x - mean);
+        m[0] = mean; m[1] = m2;
+      }
+    }
   }
   if (c < e.trace_full_chains && e.tr_full && row < e.trace_rows) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.rowlen_full; i += gridDim.x * blockDim.x)

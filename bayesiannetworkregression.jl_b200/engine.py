@@ -115,6 +115,12 @@ class Engine:
     def set_moment_window(self, first_sweep, length):
         check(self._L.bnr_set_moment_window(self._h, int(first_sweep), int(length)))
 
+    def set_moment_blocks(self, first_sweep, block_len, nblocks):
+        check(self._L.bnr_set_moment_blocks(self._h, int(first_sweep), int(block_len), int(nblocks)))
+
+    def moments_from_blocks(self, first_block, nblocks):
+        check(self._L.bnr_moments_from_blocks(self._h, int(first_block), int(nblocks)))
+
     def moments_from_trace(self, first_row, nrows):
         check(self._L.bnr_moments_from_trace(self._h, int(first_row), int(nrows)))
 

@@ -346,7 +346,12 @@ def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_de
 def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_delta=1.0, nu=10, mingen=10000,
                          maxgen=100000, psrf_cutoff=1.01, x_transform=True, num_chains=2, seed=None,
                          purge_burn=None, device=0, return_state="full", verbose=False, chain_offset=0):
-    """The "doubling generation" scheme (generate_samples_dbl!, src/gibbs.jl:1051-1198)."""
+    """The "doubling generation" scheme (generate_samples_dbl!, src/gibbs.jl:1051-1198).
+
+    The retained window grows by mingen/2 draws per round, so its R-hat cannot come from one fixed streaming window.
+    When mingen is a multiple of 4 every window and every split half is a whole number of blocks of mingen/4 sweeps:
+    the device keeps per-block moments (bnr_set_moment_blocks) and merges them (bnr_moments_from_blocks), and only
+    chain 1 keeps a trace.  Otherwise all chains are traced and R-hat is taken from the trace rows."""
     Xn, y = _prepare(X, y, R, nu, x_transform)
     nburn = _jround(mingen / 2)
     nsamp = mingen - nburn
@@ -357,18 +362,34 @@ def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, 
     rounds = max(0, math.ceil((maxgen - total) / max(mingen, 1)))
     capacity = max(tot_save, nsamp + (rounds + 1) * halfburn + halfburn)
     seed = random.randint(1, 55555) if seed is None else seed
+    blocked = mingen % 4 == 0 and mingen >= 8 and purge_burn is None
+    blk = mingen // 4
     eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, chain_offset=chain_offset,
                  trace_rows=capacity,
-                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=True,
-                 eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
+                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=not blocked,
+                 trace_gamma_xi_chains=1, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
     try:
+        if blocked:
+            # block b = sweeps [b blk, (b+1) blk); after round k (k = 0: the first pass) mingen (k+1) sweeps exist and
+            # the last mingen (k+1) / 2 of them are retained: blocks [2(k+1), 4(k+1))
+            eng.set_moment_blocks(0, blk, 4 * (rounds + 1))
         eng.init_state()
         _run_rows(eng, 2, nburn, total, purge_burn)
         nb = purge_burn if purge_burn is not None else nburn
         tot_generated = total
         tot_samples = nsamp
         tot_sze = tot_save
-        rx, rg = _psrf(eng, nb, nsamp)
+        k = 0
+
+        def psrf():
+            if blocked:
+                if (2 * (k + 1) * blk) // 2 < 2:
+                    return np.full(eng.V, np.nan), np.full(eng.q, np.nan)
+                eng.moments_from_blocks(2 * (k + 1), 2 * (k + 1))
+                return _psrf(eng, nb, nsamp, streamed=True)
+            return _psrf(eng, nb, nsamp)
+
+        rx, rg = psrf()
 
         def unconverged():
             mx, mg = _max(rx), _max(rg)
@@ -383,13 +404,14 @@ def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, 
             _run_rows(eng, num2move + 1, 0, new_save, purge_burn)
             tot_sze = new_save
             tot_generated += mingen
-            rx, rg = _psrf(eng, nb, nsamp)
+            k += 1
+            rx, rg = psrf()
             if verbose:
                 print("%d samples generated. Max PSRF XI: %.3f. Max PSRF Gamma: %.3f" %
                       (tot_generated, _max(rx), _max(rg)))
         state = _fetch_state(eng, tot_sze, return_state)
         extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
-                     device_summary=_device_summary(eng, nb, nsamp))
+                     device_summary=_device_summary(eng, nb, nsamp), rhat_streamed=blocked)
         return Results(state, rx, rg, nb, nsamp, extra)
     finally:
         eng.close()

@@ -169,6 +169,13 @@ int bnr_copy_trace_rows(bnr_handle* h, int64_t dst_row, int64_t src_row, int64_t
 /* Split-half streaming moments for R-hat: sweeps whose 1-based number s satisfies
  * first <= s < first+len contribute; halves are [first, first+len/2) and the last len/2 sweeps. */
 int bnr_set_moment_window(bnr_handle* h, int64_t first_sweep, int64_t len);
+/* Block moments, for R-hat windows that GROW (the doubling scheme, src/gibbs.jl:1051-1198): sweep s >= first_sweep
+ * contributes to block (s - first_sweep) / block_len (nblocks blocks; 0 switches the feature off).
+ * bnr_moments_from_blocks merges the blocks [first_block, first_block + nblocks) -- nblocks even, the first half of
+ * them forming the first split chain -- into the split-half moments buffer, after which bnr_rhat /
+ * bnr_export_moments work as usual.  No chain needs a trace for R-hat. */
+int bnr_set_moment_blocks(bnr_handle* h, int64_t first_sweep, int64_t block_len, int32_t nblocks);
+int bnr_moments_from_blocks(bnr_handle* h, int32_t first_block, int32_t nblocks);
 /* device pointer to [chain][half(2)][param(V xi then q gamma)][mean, M2] and its length in doubles */
 int bnr_moments_device(bnr_handle* h, double** dev_ptr, int64_t* count);
 /* R-hat (src/convergence.jl:4-65) from gathered moments of total_chains chains; dev_moments is a DEVICE

@@ -546,3 +546,38 @@ def test_plain_c_client_runs_a_fit(bnr, tmp_path):
     r = subprocess.run([exe, "60", "10", "3", "6", "80"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sweeps 80" in r.stdout
+
+
+def test_block_moments_equal_trace_moments(bnr):
+    """Per-block streaming moments merged over a window (what the doubling scheme uses instead of all-chain traces)
+    give the same split R-hat as the two-pass reduction of the recorded rows, for every window made of whole blocks."""
+    X, y = _toy(7, V=6, R=3, n=30)
+    blk, nblocks = 10, 12
+    with bnr.Engine(X, y, 3, num_chains=5, seed=8, trace_rows=blk * nblocks + 1) as eng:
+        eng.set_moment_blocks(0, blk, nblocks)
+        eng.init_state()
+        eng.run(37)                       # windows keep working across several bnr_run calls (graph + eager sweeps)
+        eng.run(blk * nblocks - 1 - 37)
+        for first_block, nb in ((2, 2), (4, 4), (6, 6), (0, 12)):
+            eng.moments_from_blocks(first_block, nb)
+            assert eng.moment_half_len() == nb // 2 * blk
+            rx_b, rg_b = eng.rhat()
+            eng.moments_from_trace(first_block * blk, nb * blk)        # row r holds sweep r
+            rx_t, rg_t = eng.rhat()
+            np.testing.assert_allclose(rg_b, rg_t, rtol=1e-10)
+            fin = np.isfinite(rx_t)
+            np.testing.assert_array_equal(np.isfinite(rx_b), fin)
+            np.testing.assert_allclose(rx_b[fin], rx_t[fin], rtol=1e-10)
+        with pytest.raises(bnr.BnrError):
+            eng.moments_from_blocks(0, 3)
+    # the doubling scheme on top of it: blocked (mingen % 4 == 0) and trace-based runs see the same chains
+    a = bnr.Fit(X, y, 3, mingen=40, maxgen=120, psrf_cutoff=0.0, num_chains=3, seed=3, x_transform=False, filename=None)
+    assert a.extra["rhat_streamed"] and a.extra["tot_generated"] == 120 and a.sampled == 60
+    with bnr.Engine(X, y, 3, num_chains=3, seed=3, trace_rows=120) as eng:
+        eng.init_state()
+        eng.run(119)
+        eng.moments_from_trace(60, 60)   # the last 60 of the 120 generated rows
+        _, rg = eng.rhat()
+        last = eng.get_trace(0, "gamma", 119, 120)[0, :, 0]
+    np.testing.assert_allclose(a.rhatγ.γ, rg, rtol=1e-9)
+    np.testing.assert_array_equal(a.state["γ"][-1, :, 0], last)
