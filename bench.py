@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the config's)")
+    ap.add_argument("--total-chains", type=int, default=0,
+                    help="strong scaling: this many chains in total, split evenly over the GPUs (BASELINE config 3 "
+                         "quotes 64 chains across 1/2/4/8 GPUs); default is weak scaling with the config's chains per GPU")
     ap.add_argument("--chain-groups", type=int, default=0, help="independent stream/graph groups per GPU (0 = library default)")
     ap.add_argument("--gamma-mode", default="auto", choices=["auto", "nform", "qform"])
     ap.add_argument("--dense", action="store_true", help="dense Gaussian X instead of sparse networks")
@@ -197,6 +200,11 @@ def main():
 
     X, y, dims = synth(args.config, args.dense)
     chains = args.chains or CONFIGS[args.config]["chains"]
+    scaling = "weak"
+    if args.total_chains:
+        if args.total_chains % world:
+            raise SystemExit("--total-chains must be a multiple of the GPU count")
+        chains, scaling = args.total_chains // world, "strong"
     V, q, n, R = dims["V"], dims["q"], dims["n"], dims["R"]
     K, Wm = args.steps, max(args.warmup, 3)
 
@@ -338,7 +346,7 @@ def main():
         line = {
             "metric": "gibbs_iters_per_sec_all_chains", "value": value, "unit": "chain-iterations/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, dims, chains),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "chain-iterations/s", "h2d_bytes_per_step": h2d,
