@@ -245,6 +245,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   linalg_setup();
+  small_kernels_setup();
 
   Engine& e = h->e;
   const size_t C = d.C;

@@ -56,6 +56,7 @@ void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX
 void launch_build_P(const Engine& e, cudaStream_t s);        // q-form: P_c = (X'X + diag(1/S_c)) / tau2_c
 int chol_max_dim();
 void linalg_setup();                                          // one-time cudaFuncSetAttribute calls
+void small_kernels_setup();
 
 // posterior diagnostics on the device (bnr_diagnostics.cu)
 void launch_summary_select(const double* rows, size_t rowlen, int off, int nelem, long long first, long long count,

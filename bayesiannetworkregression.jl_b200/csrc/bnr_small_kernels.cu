@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
   const Dims& d = e.d;
   const int c = blockIdx.x, tid = threadIdx.x, R = d.R, V = d.V, RR = R * R;
   double* us = sm;                 // [V*R]
-  double* psi = us + V * R;        // [RR]
-  double* sums = psi + RR;         // [2*MAX_R+1]
+  double* psi = us + V * R;        // [4 * RR]: Psi, chol(Psi), Bartlett factor, Y (M update)
+  double* sums = psi + 4 * RR;     // [2*MAX_R+1]
   double* red = sums + 2 * MAX_R + 1;  // [32]
   const long long it = *e.iter + 1;
   const InjLayout L = InjLayout::make(d.n, V, R, d.gigK);
@@ -443,40 +443,66 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
         psi[en] = s;
       }
       __syncthreads();
+      // The variates come from ONE sequential stream (thread 0, same order as before: R chi-squares, then the
+      // strictly-lower normals row by row); the R x R linear algebra is done by warp 0 in shared memory -- the
+      // single-thread version with its three local-memory R x R arrays was the longest kernel of the small configs.
+      double* Lp = psi + RR;          // chol(Psi), lower
+      double* Ab = Lp + RR;           // Bartlett factor, lower
+      double* Yw = Ab + RR;           // Y = A^-1 Lp'
+      const double df = d.nu + nz;
       if (tid == 0) {
-        const double df = d.nu + nz;
-        double Lp[MAX_R * MAX_R], Ab[MAX_R * MAX_R], Y[MAX_R * MAX_R];
-        for (int i = 0; i < RR; ++i) Lp[i] = psi[i];
-        if (!small_chol(Lp, R)) atomicOr(&e.status[c], BNR_ST_PSI_NOTPD_);
         DrawStream st(key, (uint32_t)it, SITE_M, 0, injc ? injc + L.M : nullptr, R + R * (R - 1) / 2);
-        // Bartlett factor A (lower): A_ii = sqrt(chi2(df - i)), A_ij ~ N(0,1) (j < i)
         for (int i = 0; i < R; ++i) {
           const double ci = injc ? st.uniform() : 2.0 * st.gamma(0.5 * (df - i));
           Ab[i + R * i] = sqrt(ci);
         }
         for (int i = 0; i < R; ++i)
           for (int j = 0; j < i; ++j) Ab[i + R * j] = st.normal();
-        // Y = A^-1 Lp'  (forward substitution, column by column); M = Y' Y
-        for (int col = 0; col < R; ++col)
+      }
+      for (int i = tid; i < RR; i += blockDim.x) Lp[i] = psi[i];
+      __syncthreads();
+      if (tid < 32) {
+        const int lane = tid;
+        // Cholesky of Psi, column by column: lane i owns row i (same summation order as small_chol)
+        bool ok = true;
+        for (int j = 0; j < R; ++j) {
+          double sdot = 0.0;
+          if (lane >= j && lane < R) {
+            sdot = Lp[lane + R * j];
+            for (int p = 0; p < j; ++p) sdot -= Lp[lane + R * p] * Lp[j + R * p];
+          }
+          const double dj = __shfl_sync(0xffffffffu, sdot, j);
+          if (!(dj > 0.0)) ok = false;
+          const double rt = sqrt(dj);
+          if (lane == j) Lp[j + R * j] = rt;
+          else if (lane > j && lane < R) Lp[lane + R * j] = sdot / rt;
+          __syncwarp();
+        }
+        if (!ok && lane == 0) atomicOr(&e.status[c], BNR_ST_PSI_NOTPD_);
+        // Y = A^-1 Lp'  (forward substitution; lane = column), then M = Y' Y (lanes over the R^2 entries)
+        if (lane < R) {
+          const int col = lane;
           for (int i = 0; i < R; ++i) {
-            double s = (col >= i) ? Lp[col + R * i] : 0.0;   // Lp'(i, col) = Lp(col, i)
-            for (int p = 0; p < i; ++p) s -= Ab[i + R * p] * Y[p + R * col];
-            Y[i + R * col] = s / Ab[i + R * i];
+            double sv = (col >= i) ? Lp[col + R * i] : 0.0;   // Lp'(i, col) = Lp(col, i)
+            for (int p = 0; p < i; ++p) sv -= Ab[i + R * p] * Yw[p + R * col];
+            Yw[i + R * col] = sv / Ab[i + R * i];
           }
-        for (int a = 0; a < R; ++a)
-          for (int b = 0; b < R; ++b) {
-            double s = 0.0;
-            for (int p = 0; p < R; ++p) s += Y[p + R * a] * Y[p + R * b];
-            e.M[(size_t)c * RR + a + R * b] = s;
-          }
+        }
+        __syncwarp();
+        for (int en = lane; en < RR; en += 32) {
+          const int a = en % R, b = en / R;
+          double sv = 0.0;
+          for (int p = 0; p < R; ++p) sv += Yw[p + R * a] * Yw[p + R * b];
+          e.M[(size_t)c * RR + a + R * b] = sv;
+        }
         if (e.aux.m_params) {
           double* o = e.aux.m_params + (size_t)c * (1 + 2 * RR);
-          o[0] = df;
-          for (int a = 0; a < R; ++a)
-            for (int b = 0; b < R; ++b) {
-              o[1 + a + R * b] = psi[a + R * b];
-              o[1 + RR + a + R * b] = (a >= b) ? Lp[a + R * b] : 0.0;
-            }
+          if (lane == 0) o[0] = df;
+          for (int en = lane; en < RR; en += 32) {
+            const int a = en % R, b = en / R;
+            o[1 + a + R * b] = psi[a + R * b];
+            o[1 + RR + a + R * b] = (a >= b) ? Lp[a + R * b] : 0.0;
+          }
         }
       }
     }
@@ -751,6 +777,18 @@ __global__ void k_rng_dump(Dims d, int chain, long long iteration, int site, int
 // ------------------------------------------------------------------------------------------------------------
 static size_t smem_u(const Dims& d) { return sizeof(double) * ((size_t)d.V * d.R + d.R + 64); }
 
+// the per-chain kernels keep u (V x R doubles) in dynamic shared memory: allow more than the 48 KB default
+// (bnr_create rejects problems beyond 200 KB)
+void small_kernels_setup() {
+  const int lim = 200 * 1024;
+  cudaFuncSetAttribute(k_tau2, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_uxi, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_edge_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_gamma_gig, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+  cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
 void launch_tau2(const Engine& e, cudaStream_t s) {
   ++g_launches; k_tau2<<<e.d.C, 256, smem_u(e.d), s>>>(e);
 }
@@ -775,7 +813,7 @@ void launch_gamma_gig(const Engine& e, int flags, cudaStream_t s) {
   ++g_launches; k_gamma_gig<<<grid, PART_BLOCK, sm, s>>>(e, flags);
 }
 void launch_finish(const Engine& e, int mask, cudaStream_t s) {
-  const size_t sm = sizeof(double) * ((size_t)e.d.V * e.d.R + e.d.R * e.d.R + 2 * MAX_R + 1 + 32);
+  const size_t sm = sizeof(double) * ((size_t)e.d.V * e.d.R + 4 * e.d.R * e.d.R + 2 * MAX_R + 1 + 32);
   ++g_launches; k_finish<<<e.d.C, 256, sm, s>>>(e, mask);
 }
 void launch_init(const Engine& e, cudaStream_t s) {
