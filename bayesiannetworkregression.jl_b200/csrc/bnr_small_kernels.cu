@@ -46,6 +46,26 @@ __device__ bool small_chol(double* A, int R) {
   return true;
 }
 
+// the same factorisation by one warp (lane i owns row i; identical summation order, so identical results): A is a
+// col-major R x R SPD matrix in shared memory, R <= 32.  Every lane returns whether all pivots were positive.
+__device__ bool warp_chol(double* A, int R, int lane) {
+  bool ok = true;
+  for (int j = 0; j < R; ++j) {
+    double s = 0.0;
+    if (lane >= j && lane < R) {
+      s = A[lane + R * j];
+      for (int p = 0; p < j; ++p) s -= A[lane + R * p] * A[j + R * p];
+    }
+    const double dj = __shfl_sync(0xffffffffu, s, j);
+    if (!(dj > 0.0)) ok = false;
+    const double rt = sqrt(dj);
+    if (lane == j) A[j + R * j] = rt;
+    else if (lane > j && lane < R) A[lane + R * j] = s / rt;
+    __syncwarp();
+  }
+  return ok;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // tau^2  (update_tau2!, src/gibbs.jl:267-277): InverseGamma(n/2 + q/2, 1/2 |y - mu - X gamma|^2 + 1/2 sum (gamma-W)^2/S)
 // grid = C, block = 256.  X gamma comes from the cache e.xg.
@@ -121,30 +141,34 @@ __global__ void __launch_bounds__(32 * UXI_WARPS) k_uxi(Engine e) {
   for (int i = tid; i < V * R; i += blockDim.x) ulam[i] = up[i] * e.lambda[c * R + (i % R)];
   for (int i = tid; i < RR; i += blockDim.x) Mch[i] = e.M[(size_t)c * RR + i];
   __syncthreads();
-  if (tid == 0) {
-    // M^-1 and logdet M through the Cholesky factor of M
-    const bool ok = small_chol(Mch, R);
-    double ld = 0.0;
-    for (int i = 0; i < R; ++i) ld += log(Mch[i + R * i]);
-    misc[0] = 2.0 * ld;
-    misc[1] = ok ? 1.0 : 0.0;
-    // invert L (lower) in place into Minv as Linv, then Minv = Linv' Linv
-    double Li[MAX_R * MAX_R];
-    for (int j = 0; j < R; ++j) {
-      for (int i = 0; i < R; ++i) Li[i + R * j] = 0.0;
+  if (tid < 32) {
+    // M^-1 and logdet M through the Cholesky factor of M, by warp 0: chol, then lane j inverts column j of L
+    // (forward substitution, written over Minv as Linv), then Minv = Linv' Linv with the lanes over its entries
+    const bool ok = warp_chol(Mch, R, lane);
+    double* Li = A0;                        // warp 0's own scratch (its per-node use starts after the barrier)
+    if (lane < R) {
+      const int j = lane;
+      for (int i = 0; i < j; ++i) Li[i + R * j] = 0.0;
       Li[j + R * j] = 1.0 / Mch[j + R * j];
       for (int i = j + 1; i < R; ++i) {
-        double s = 0.0;
-        for (int p = j; p < i; ++p) s -= Mch[i + R * p] * Li[p + R * j];
-        Li[i + R * j] = s / Mch[i + R * i];
+        double sv = 0.0;
+        for (int p = j; p < i; ++p) sv -= Mch[i + R * p] * Li[p + R * j];
+        Li[i + R * j] = sv / Mch[i + R * i];
       }
     }
-    for (int a = 0; a < R; ++a)
-      for (int b = 0; b < R; ++b) {
-        double s = 0.0;
-        for (int p = (a > b ? a : b); p < R; ++p) s += Li[p + R * a] * Li[p + R * b];
-        Minv[a + R * b] = s;
-      }
+    __syncwarp();
+    for (int en = lane; en < RR; en += 32) {
+      const int a = en % R, b = en / R;
+      double sv = 0.0;
+      for (int p = (a > b ? a : b); p < R; ++p) sv += Li[p + R * a] * Li[p + R * b];
+      Minv[en] = sv;
+    }
+    if (lane == 0) {
+      double ld = 0.0;
+      for (int i = 0; i < R; ++i) ld += log(Mch[i + R * i]);
+      misc[0] = 2.0 * ld;
+      misc[1] = ok ? 1.0 : 0.0;
+    }
   }
   __syncthreads();
 
@@ -180,24 +204,30 @@ __global__ void __launch_bounds__(32 * UXI_WARPS) k_uxi(Engine e) {
     }
   }
   __syncwarp();
-  if (lane == 0) {
-    int status = 0;
-    if (misc[1] == 0.0) status |= BNR_ST_SIGMA_NOTPD_;
-    for (int i = 0; i < RR; ++i) A0[i] = A[i];
-    // jitter ladder of the reference (src/gibbs.jl:322-347): +1e-5 I, then a further +4e-5 I
-    bool ok = small_chol(A, R);
+  // Cholesky of Sigma^-1 with the reference's jitter ladder (src/gibbs.jl:322-347: +1e-5 I, then a further +4e-5 I),
+  // by the whole warp; the O(R^2) solves and the sequential draws stay with lane 0
+  int status = 0;
+  if (misc[1] == 0.0) status |= BNR_ST_SIGMA_NOTPD_;
+  for (int i = lane; i < RR; i += 32) A0[i] = A[i];
+  __syncwarp();
+  bool ok = warp_chol(A, R, lane);
+  if (!ok) {
+    status |= BNR_ST_JITTER_;
+    if (lane < R) A0[lane + R * lane] += 1e-5;
+    __syncwarp();
+    for (int i = lane; i < RR; i += 32) A[i] = A0[i];
+    __syncwarp();
+    ok = warp_chol(A, R, lane);
     if (!ok) {
-      status |= BNR_ST_JITTER_;
-      for (int i = 0; i < R; ++i) A0[i + R * i] += 1e-5;
-      for (int i = 0; i < RR; ++i) A[i] = A0[i];
-      ok = small_chol(A, R);
-      if (!ok) {
-        for (int i = 0; i < R; ++i) A0[i + R * i] += 4e-5;
-        for (int i = 0; i < RR; ++i) A[i] = A0[i];
-        ok = small_chol(A, R);
-        if (!ok) status |= BNR_ST_SIGMA_NOTPD_;
-      }
+      if (lane < R) A0[lane + R * lane] += 4e-5;
+      __syncwarp();
+      for (int i = lane; i < RR; i += 32) A[i] = A0[i];
+      __syncwarp();
+      ok = warp_chol(A, R, lane);
+      if (!ok) status |= BNR_ST_SIGMA_NOTPD_;
     }
+  }
+  if (lane == 0) {
     // mu_t = Sigma b : solve L w = b, L' mu_t = w
     double ldA = 0.0;
     for (int i = 0; i < R; ++i) {
