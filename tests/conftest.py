@@ -35,4 +35,9 @@ def golden():
 
 @pytest.fixture(scope="session")
 def bnr():
+    so = os.path.join(ROOT, "bayesiannetworkregression.jl_b200", "libbnr.so")
+    if not os.path.exists(so):
+        # a fresh checkout: build the library first (nvcc cross-compiles sm_100a without a GPU)
+        import subprocess
+        subprocess.run(["make", "-j4", "-C", ROOT], check=True)
     return load_package()
