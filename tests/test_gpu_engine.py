@@ -581,3 +581,36 @@ def test_block_moments_equal_trace_moments(bnr):
         last = eng.get_trace(0, "gamma", 119, 120)[0, :, 0]
     np.testing.assert_allclose(a.rhatγ.γ, rg, rtol=1e-9)
     np.testing.assert_array_equal(a.state["γ"][-1, :, 0], last)
+
+
+@pytest.mark.parametrize("V,n,R,mode", [(40, 3000, 4, "nform"), (60, 2000, 5, "qform"), (300, 300, 9, "nform")])
+def test_unusual_shapes_factorisation_properties(bnr, V, n, R, mode):
+    """Tall n-form (24 panels of 128), long q-form (15 panels) and a large network (q = 45150): the factored matrix
+    satisfies L L' = G (resp. P) and G a4 = rhs-type residuals stay at rounding level; chains stay healthy."""
+    rng = np.random.default_rng(V + n)
+    q = V * (V + 1) // 2
+    X = rng.normal(size=(n, q)) * (rng.random((n, q)) < 0.4)
+    y = 3 + X[:, :12].sum(axis=1) + rng.normal(size=n)
+    with bnr.Engine(X, y, R, num_chains=2, seed=1, gamma_mode=mode) as eng:
+        assert eng.gamma_mode == mode
+        eng.init_state()
+        eng.run(3)
+        eng.enable_aux(True)
+        S_old = eng.get_state(1, "S")[:, 0].copy()
+        eng.step("tau2"); eng.step("u_xi"); eng.step("gamma")
+        tau2 = float(eng.get_state(1, "tau2")[0, 0])
+        m = q if mode == "qform" else n
+        G = eng.get_aux(1, "G").reshape(m, m).T
+        L = eng.get_aux(1, "G_chol").reshape(m, m).T
+        want = (X.T @ X + np.diag(1.0 / S_old)) / tau2 if mode == "qform" else (X * S_old[None, :]) @ X.T + np.eye(n)
+        scale = np.abs(want).max()
+        assert np.abs(G - want).max() <= 1e-12 * scale
+        assert np.abs(L @ L.T - want).max() <= 1e-11 * scale
+        for cond in ("D", "theta", "Delta", "M", "mu", "lam", "pi"):
+            eng.step(cond)
+        eng.finish_sweep()
+        eng.enable_aux(False)
+        eng.run(4)
+        st = eng.get_state_dict(0)
+        assert not (eng.status() & ~1).any()
+        assert np.isfinite(st["gamma"]).all() and (st["S"] > 0).all() and st["tau2"] > 0
