@@ -357,7 +357,10 @@ def main():
             "roofline": {"bound": "tensor", "kernel": dom_kernel,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": traffic, "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
-                         "peak_source": "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+                         "peak_source": "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_theoretical": 128 * 148 * 1.965e9 / 1e12,
+                         "frac_of_theoretical": achieved / (128 * 148 * 1.965e9 / 1e12),
+                         "note": "theoretical = 128 FP64 flop/clk/SM (DMMA and DFMA alike) x 148 SMs x 1.965 GHz"},
             "cpu_baseline": cpu,
             "gamma_ess_per_sec": {"median": ess_med / (total_ms * 1e-3),
                                   "min": ess_min / (total_ms * 1e-3),
