@@ -758,22 +758,25 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
   __syncthreads();
 
   if (warp == 8) {
-    if (lane == 0) {
-      int it = 0;
-      for (int J = T - 1; J >= 0; --J)
-        for (int I = T - 1; I >= J; --I)            // I == J: the diagonal block, taken from Linv, comes last
-          for (int h = 0; h < 2; ++h, ++it) {
-            const int stage = it % nstages;
+    // lane 0 owns the hand-shake; the 32 lanes then issue the 64 bulk copies of the stage two each (a single lane
+    // needs longer to issue them than the consumers need to use them)
+    int it = 0;
+    for (int J = T - 1; J >= 0; --J)
+      for (int I = T - 1; I >= J; --I)            // I == J: the diagonal block, taken from Linv, comes last
+        for (int h = 0; h < 2; ++h, ++it) {
+          const int stage = it % nstages;
+          double* dst = ring + (size_t)stage * BW_STAGE_DBL;
+          if (lane == 0) {
             mbar_wait(&empty[stage], ((it / nstages) & 1) ^ 1);
-            double* dst = ring + (size_t)stage * BW_STAGE_DBL;
             mbar_expect_tx(&full[stage], BW_STAGE_DBL * 8);
-            const double* src = (I == J) ? Lc + (size_t)J * PB * PB + (size_t)h * BW_COLS * PB
-                                         : Gc + (size_t)(J * PB + h * BW_COLS) * N + (size_t)I * PB;
-            const size_t cs = (I == J) ? PB : N;
-#pragma unroll 4
-            for (int col = 0; col < BW_COLS; ++col) bulk_g2s(dst + col * PB, src + col * cs, PB * 8, &full[stage]);
           }
-    }
+          __syncwarp();
+          const double* src = (I == J) ? Lc + (size_t)J * PB * PB + (size_t)h * BW_COLS * PB
+                                       : Gc + (size_t)(J * PB + h * BW_COLS) * N + (size_t)I * PB;
+          const size_t cs = (I == J) ? PB : N;
+#pragma unroll
+          for (int col = lane; col < BW_COLS; col += 32) bulk_g2s(dst + col * PB, src + col * cs, PB * 8, &full[stage]);
+        }
     return;
   }
 
