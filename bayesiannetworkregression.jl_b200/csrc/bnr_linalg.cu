@@ -727,14 +727,20 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
 //   off-diagonal block (I, J): b_J -= L[I, J]' x_I          diagonal block J: x_J = Linv_J' b_J
 // grid = C, block = 288 (8 consumer warps + 1 producer warp).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int BW_COLS = 64;
+#ifndef BNR_BW_COLS
+#define BNR_BW_COLS 64
+#endif
+constexpr int BW_COLS = BNR_BW_COLS;             // columns per staged part of a 128 x 128 block
+constexpr int BW_NH = PB / BW_COLS;              // parts per block
+constexpr int BW_CPW = BW_COLS / 8;              // columns per consumer warp
+constexpr int BW_MAX_STAGES = (192 / BW_COLS) < 8 ? (192 / BW_COLS) : 8;   // at most 192 KB of ring, 8 barriers
 constexpr int BW_STAGE_DBL = BW_COLS * PB;
 static int bwd_stages(int N) {
   const size_t budget = 227 * 1024 - sizeof(double) * (size_t)N - 256;
   int ns = (int)(budget / (sizeof(double) * BW_STAGE_DBL));
-  return ns > 3 ? 3 : ns;
+  return ns > BW_MAX_STAGES ? BW_MAX_STAGES : ns;
 }
-static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 128; }
+static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 160; }
 
 __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G, size_t chain_stride, int N, int m,
                                                     const double* __restrict__ Linv, double* __restrict__ out,
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
   double* ring = sm;
   double* x = sm + (size_t)nstages * BW_STAGE_DBL;     // [N] right-hand side, overwritten block by block by x
   unsigned long long* full = reinterpret_cast<unsigned long long*>(x + N);
-  unsigned long long* empty = full + 4;
+  unsigned long long* empty = full + 8;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = N / PB;
   const double* Gc = G + (size_t)c * chain_stride;
@@ -763,7 +769,7 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
     int it = 0;
     for (int J = T - 1; J >= 0; --J)
       for (int I = T - 1; I >= J; --I)            // I == J: the diagonal block, taken from Linv, comes last
-        for (int h = 0; h < 2; ++h, ++it) {
+        for (int h = 0; h < BW_NH; ++h, ++it) {
           const int stage = it % nstages;
           double* dst = ring + (size_t)stage * BW_STAGE_DBL;
           if (lane == 0) {
@@ -781,7 +787,7 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
   }
 
   int it = 0;
-  double xn[2][8];                                   // diagonal-block results of this warp's columns (both halves)
+  double xn[BW_NH][BW_CPW];                          // diagonal-block results of this warp's columns (all parts)
   for (int J = T - 1; J >= 0; --J) {
     for (int I = T - 1; I >= J; --I) {
       const bool dg = (I == J);
@@ -789,37 +795,37 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
       const double* v = x + I * PB;
       const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
 #pragma unroll
-      for (int h = 0; h < 2; ++h, ++it) {
+      for (int h = 0; h < BW_NH; ++h, ++it) {
         const int stage = it % nstages;
         mbar_wait(&full[stage], (it / nstages) & 1);
-        const double* B = ring + (size_t)stage * BW_STAGE_DBL + (size_t)(warp * 8) * PB + lane;
-        double acc[8];
+        const double* B = ring + (size_t)stage * BW_STAGE_DBL + (size_t)(warp * BW_CPW) * PB + lane;
+        double acc[BW_CPW];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < BW_CPW; ++q)
           acc[q] = B[q * PB] * v0 + B[q * PB + 32] * v1 + B[q * PB + 64] * v2 + B[q * PB + 96] * v3;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < BW_CPW; ++q) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
         }
         if (dg) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) xn[h][q] = acc[q];
+          for (int q = 0; q < BW_CPW; ++q) xn[h][q] = acc[q];
         } else if (lane == 0) {
-          double* bj = x + J * PB + h * BW_COLS + warp * 8;
+          double* bj = x + J * PB + h * BW_COLS + warp * BW_CPW;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) bj[q] -= acc[q];
+          for (int q = 0; q < BW_CPW; ++q) bj[q] -= acc[q];
         }
       }
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");               // everybody has read b_J
     if (lane == 0) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < BW_NH; ++h)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) x[J * PB + h * BW_COLS + warp * 8 + q] = xn[h][q];
+        for (int q = 0; q < BW_CPW; ++q) x[J * PB + h * BW_COLS + warp * BW_CPW + q] = xn[h][q];
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");               // x_J visible to the next block column
   }
