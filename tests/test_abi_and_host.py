@@ -208,3 +208,22 @@ def test_header_is_plain_c_and_links(bnr, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test / bench infrastructure: nothing under the package may import, call or link it, and the
+    package has no CPU fallback path (every numerical entry point goes through libbnr.so)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "bayesiannetworkregression.jl_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), encoding="utf8").read()
+                for line in text.splitlines():
+                    code = line.split("#")[0].split("//")[0]
+                    if re.search(r"\b(import|from)\s+oracle\b|oracle\.|oracle/", code):
+                        offenders.append((f, line.strip()))
+    assert not offenders, offenders
+    eng_src = open(os.path.join(pkg, "engine.py"), encoding="utf8").read()
+    assert "numpy.linalg" not in eng_src and "np.linalg" not in eng_src and "scipy" not in eng_src
