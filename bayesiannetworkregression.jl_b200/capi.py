@@ -72,6 +72,11 @@ PROTOTYPES = {
     "bnr_export_ess": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "bnr_ess_from_stats": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int64, C.c_int32, _DP, _DP]),
+    "bnr_ess_from_stats_lags": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int64, C.c_int32, _DP, _DP, _DP, _DP]),
+    "bnr_ess_stream_begin": (C.c_int, [_H, C.c_int32, C.c_int64]),
+    "bnr_ess_stream_finish": (C.c_int, [_H]),
+    "bnr_chain_groups": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_gamma_mode": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "bnr_launch_count": (C.c_int, [_H, _I64P]),
     "bnr_profile_sweep": (C.c_int, [_H, C.POINTER(C.c_float)]),

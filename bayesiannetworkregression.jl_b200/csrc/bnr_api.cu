@@ -49,7 +49,7 @@ struct ChainGroup {
   long long* counters = nullptr; // device [2]: iter, trace_row of this group
   long long* mom_window = nullptr;
 };
-constexpr int MAX_GROUPS = 4;
+constexpr int MAX_GROUPS = 8;
 
 // ---------------------------------------------------------------------------------------------------------
 // Device-memory cache.  Releasing gigabytes with cudaFree costs 30 - 300 ms (occasionally seconds) and synchronises
@@ -122,6 +122,11 @@ struct bnr_handle {
   int ess_lag = -1;
   long long ess_rows = 0;
   size_t acov_cap = 0;
+  // streaming ESS (bnr_ess_stream_begin / _finish)
+  long long* d_esswin = nullptr; // device [4]
+  double* ess_stream_buf = nullptr;  // ring | head | lagged products | sums, reused across begin calls
+  size_t ess_stream_cap = 0;     // its capacity in doubles
+  long long ess_stream_N = 0;    // > 0 while a streaming window is armed
 };
 
 static int raw_alloc(bnr_handle* h, void** out, size_t bytes) {
@@ -131,6 +136,29 @@ static int raw_alloc(bnr_handle* h, void** out, size_t bytes) {
   *out = p;
   return 0;
 }
+
+// hand a buffer that a larger one supersedes back to the cache (instead of keeping it until bnr_destroy)
+static void release_alloc(bnr_handle* h, void* p) {
+  if (!p) return;
+  for (size_t i = 0; i < h->allocs.size(); ++i)
+    if (h->allocs[i].first == p) {
+      cache_give(h->p.device, p, h->allocs[i].second);
+      h->allocs[i] = h->allocs.back();
+      h->allocs.pop_back();
+      return;
+    }
+}
+
+// short-lived device scratch of the handle-less entry points (bnr_rhat_from_moments, bnr_ess_from_stats): taken from
+// and returned to the process-wide cache, so the steady state performs no cudaMalloc / cudaFree
+struct Scratch {
+  int device; void* p = nullptr; size_t bytes = 0;
+  Scratch(int dev, size_t b) : device(dev), bytes((b + 255) / 256 * 256) {
+    p = cache_take(device, bytes);
+    if (!p && cudaMalloc(&p, bytes) != cudaSuccess) p = nullptr;
+  }
+  ~Scratch() { if (p) cache_give(device, p, bytes); }
+};
 
 template <typename T>
 static int dalloc(bnr_handle* h, T** ptr, size_t count, bool zero = true) {
@@ -233,6 +261,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   }
   d.nparts = (d.q + PART_BLOCK - 1) / PART_BLOCK;
   d.chain_offset = p->chain_offset;
+  d.chain_offset_local = 0;
   d.gigK = h->p.gig_inject_len;
   d.seed = p->seed;
   d.eta = p->eta; d.zeta = p->zeta; d.iota = p->iota; d.a_delta = p->a_delta; d.b_delta = p->b_delta; d.nu = p->nu;
@@ -305,11 +334,15 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     e.XtX = dXtX;
   }
   DA(e.partials, C * d.nparts * (2 * MAX_R + 1));
+  DA(e.tau2_part, C * 2 * TAU2_MAX_BLOCKS);
+  DA(e.tau2_ticket, C);
   DA(e.status, C);
   DA(e.iter, 1); DA(e.trace_row, 1);
   DA(e.moments, C * 2 * (d.V + d.q) * 2);
   DA(e.mom_window, 5);
   e.bmom = nullptr; e.bmom_nb = 0;
+  e.ess_ring = e.ess_head = e.ess_acc = e.ess_sum = nullptr; e.ess_win = nullptr; e.ess_L = e.ess_cap = 0;
+  DA(h->d_esswin, 4);
   DA(h->ws, x_times_workspace_doubles(d));
   DA(h->d_rhat, (size_t)(d.V + d.q));
   e.trace_full_chains = p->trace_rows > 0 ? (p->trace_full_chains < d.C ? p->trace_full_chains : d.C) : 0;
@@ -332,16 +365,27 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   }
   {
     // chain groups (see ChainGroup): 2 by default once there are enough chains to split
-    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 4 ? 2 : 1);
+    // default: 2 groups once the SYRK of half the chains fills the GPU for several waves; 4 when the chains are few
+    // (then the per-group latency chain, not the tensor pipe, bounds the sweep and more of them must overlap)
+    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 64 ? 2 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > d.C) ng = d.C;
     h->n_groups = ng;
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     const bool use_side = getenv("BNR_NO_SIDE") == nullptr;
+    // event pool of the Cholesky's lookahead schedule: 4 per panel (launch_cholesky)
+    auto make_pool = [&](ForkJoin& f) -> int {
+      f.npool = 4 * (d.gdim / TILE_N);
+      f.pool = new cudaEvent_t[f.npool]();
+      for (int i = 0; i < f.npool; ++i) CK(cudaEventCreateWithFlags(&f.pool[i], cudaEventDisableTiming));
+      return 0;
+    };
     if (use_side) {
       CK(cudaStreamCreateWithFlags(&h->fj.side, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&h->fj.side_hi, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&h->fj.fork, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->fj.join, cudaEventDisableTiming));
+      if (int r = make_pool(h->fj)) return r;
     }
     for (int g = 0; g < ng; ++g) {
       ChainGroup& G = h->groups[g];
@@ -353,8 +397,10 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
       CK(cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming));
       if (use_side) {
         CK(cudaStreamCreateWithPriority(&G.fj.side, cudaStreamNonBlocking, plo));
+        CK(cudaStreamCreateWithPriority(&G.fj.side_hi, cudaStreamNonBlocking, prio));
         CK(cudaEventCreateWithFlags(&G.fj.fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&G.fj.join, cudaEventDisableTiming));
+        if (int r = make_pool(G.fj)) return r;
       }
       DA(G.ws, x_times_workspace_doubles(d));
       DA(G.counters, 2);
@@ -370,6 +416,13 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
 }
 
 static void drop_graph(bnr_handle* h);
+static void drop_pool(ForkJoin& f) {
+  if (!f.pool) return;
+  for (int i = 0; i < f.npool; ++i)
+    if (f.pool[i]) cudaEventDestroy(f.pool[i]);
+  delete[] f.pool;
+  f.pool = nullptr; f.npool = 0;
+}
 
 extern "C" int bnr_trim_cache(void) {
   std::vector<CacheBlock> blocks;
@@ -401,10 +454,14 @@ extern "C" int bnr_destroy(bnr_handle* h) {
     if (h->groups[g].stream) { cudaStreamSynchronize(h->groups[g].stream); cudaStreamDestroy(h->groups[g].stream); }
     if (h->groups[g].done) cudaEventDestroy(h->groups[g].done);
     if (h->groups[g].fj.side) cudaStreamDestroy(h->groups[g].fj.side);
+    if (h->groups[g].fj.side_hi) cudaStreamDestroy(h->groups[g].fj.side_hi);
     if (h->groups[g].fj.fork) cudaEventDestroy(h->groups[g].fj.fork);
     if (h->groups[g].fj.join) cudaEventDestroy(h->groups[g].fj.join);
+    drop_pool(h->groups[g].fj);
   }
+  drop_pool(h->fj);
   if (h->fj.side) cudaStreamDestroy(h->fj.side);
+  if (h->fj.side_hi) cudaStreamDestroy(h->fj.side_hi);
   if (h->fj.fork) cudaEventDestroy(h->fj.fork);
   if (h->fj.join) cudaEventDestroy(h->fj.join);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -478,6 +535,7 @@ static void enqueue_sweep(Engine& e, double* ws, const ForkJoin& fj, cudaStream_
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
                        (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
   launch_record(e, 1, s);
+  if (e.ess_ring) launch_ess_stream(e, s);
   launch_advance(e, 1, s);
 }
 
@@ -489,6 +547,7 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   const size_t c = (size_t)c0;
   v.d.C = Cg;
   v.d.chain_offset = d.chain_offset + c0;
+  v.d.chain_offset_local = c0;
   v.tau2 += c; v.theta += c; v.Delta += c; v.mu += c; v.status += c;
   v.u += c * d.V * d.R; v.u_alt += c * d.V * d.R; v.xi += c * d.V;
   v.gamma += c * d.qp; v.S += c * d.qp; v.W += c * d.qp; v.v += c * d.qp; v.t += c * d.qp;
@@ -498,6 +557,11 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
   v.partials += c * d.nparts * (2 * MAX_R + 1);
   v.moments += c * 2 * (d.V + d.q) * 2;
   if (v.bmom) v.bmom += c * (size_t)v.bmom_nb * (d.V + d.q) * 2;
+  if (v.ess_ring) {
+    const size_t P = (size_t)d.V + d.q;
+    v.ess_ring += c * (size_t)v.ess_cap * P; v.ess_head += c * (size_t)v.ess_L * P;
+    v.ess_acc += c * (size_t)(v.ess_L + 1) * P; v.ess_sum += c * 2 * P;
+  }
   int tgc = h->e.trace_gx_chains - c0;
   tgc = tgc < 0 ? 0 : (tgc > Cg ? Cg : tgc);
   v.trace_gx_chains = tgc;
@@ -692,6 +756,8 @@ extern "C" int bnr_set_moment_blocks(bnr_handle* h, int64_t first_sweep, int64_t
     CK(cudaStreamSynchronize(h->stream));
     drop_graph(h);                       // the group views carry the buffer pointer and its block capacity
     void* p = nullptr;
+    release_alloc(h, h->e.bmom);
+    h->e.bmom = nullptr; h->e.bmom_nb = 0;
     int r = raw_alloc(h, &p, sizeof(double) * (size_t)d.C * nblocks * (d.V + d.q) * 2);
     if (r) return r;
     h->e.bmom = (double*)p;
@@ -746,13 +812,12 @@ extern "C" int bnr_rhat_from_moments(int device, const double* dev_moments, int3
                                      int32_t q, int64_t half_len, double* rhat_xi, double* rhat_gamma) {
   if (!dev_moments || total_chains < 1 || half_len < 2) return fail(BNR_EINVAL, "bad arguments (need half_len >= 2)");
   CK(cudaSetDevice(device));
-  double* d_out = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(double) * (V + q)));
+  Scratch sc(device, sizeof(double) * (V + q));
+  if (!sc.p) return fail(BNR_ENOMEM, "device scratch allocation failed");
+  double* d_out = (double*)sc.p;
   launch_rhat(dev_moments, total_chains, V + q, half_len, d_out, 0);
   std::vector<double> host(V + q);
-  cudaError_t err = cudaMemcpy(host.data(), d_out, sizeof(double) * (V + q), cudaMemcpyDeviceToHost);
-  cudaFree(d_out);
-  CK(err);
+  CK(cudaMemcpy(host.data(), d_out, sizeof(double) * (V + q), cudaMemcpyDeviceToHost));
   if (rhat_xi) memcpy(rhat_xi, host.data(), sizeof(double) * V);
   if (rhat_gamma) memcpy(rhat_gamma, host.data() + V, sizeof(double) * q);
   return BNR_OK;
@@ -945,6 +1010,8 @@ extern "C" int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_c
   const size_t total = (size_t)per_chain * h->e.d.C;
   if ((long long)total > h->inj_len) {
     void* p = nullptr;
+    release_alloc(h, h->d_inj);
+    h->d_inj = nullptr; h->inj_len = 0;
     int r = raw_alloc(h, &p, total * sizeof(double));
     if (r) return r;
     h->d_inj = (double*)p;
@@ -1082,6 +1149,7 @@ extern "C" int bnr_step(bnr_handle* h, int32_t cond) {
 extern "C" int bnr_finish_sweep(bnr_handle* h) {
   if (!h) return fail(BNR_EINVAL, "null handle");
   launch_record(h->e, 1, h->stream);
+  if (h->e.ess_ring) launch_ess_stream(h->e, h->stream);
   launch_advance(h->e, 1, h->stream);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
@@ -1170,6 +1238,8 @@ extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrow
   const size_t need = (size_t)(max_lag + 1) * P;
   if (need > h->acov_cap) {
     void* pnew = nullptr;
+    release_alloc(h, h->d_acov);
+    h->d_acov = nullptr; h->acov_cap = 0;
     int r = raw_alloc(h, &pnew, need * sizeof(double));
     if (r) return r;
     h->d_acov = (double*)pnew;
@@ -1182,6 +1252,80 @@ extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrow
   CK(cudaStreamSynchronize(h->stream));
   h->ess_lag = max_lag;
   h->ess_rows = nrows;
+  return BNR_OK;
+}
+
+// Streaming variant: the next `ndraws` sweeps contribute their lagged products while they run (k_ess_stream), so no
+// chain needs a trace.  bnr_ess_stream_finish turns the accumulators into the same two statistics buffers.
+extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndraws) {
+  if (!h || ndraws < 4 || max_lag < 1) return fail(BNR_EINVAL, "bad arguments (need ndraws >= 4, max_lag >= 1)");
+  CK(cudaSetDevice(h->p.device));
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  if (max_lag > ndraws - 1) max_lag = (int32_t)(ndraws - 1);
+  if (!(max_lag & 1)) max_lag -= 1;
+  if (max_lag < 1) max_lag = 1;
+  const int L = max_lag, cap = L + 8;
+  const size_t P = (size_t)d.V + d.q, C = d.C;
+  CK(cudaStreamSynchronize(h->stream));
+  drop_graph(h);                         // the sweep graphs gain (or keep) the k_ess_stream node and its pointers
+  const size_t need = C * P * ((size_t)cap + L + (L + 1) + 2);
+  if (need > h->ess_stream_cap) {
+    void* pnew = nullptr;
+    release_alloc(h, h->ess_stream_buf);
+    h->ess_stream_buf = nullptr; h->ess_stream_cap = 0;
+    int r = raw_alloc(h, &pnew, need * sizeof(double));
+    if (r) return r;
+    h->ess_stream_cap = need;
+    h->ess_stream_buf = (double*)pnew;
+  }
+  e.ess_ring = h->ess_stream_buf;
+  e.ess_head = e.ess_ring + C * P * cap;
+  e.ess_acc = e.ess_head + C * P * L;
+  e.ess_sum = e.ess_acc + C * P * (L + 1);
+  e.ess_L = L; e.ess_cap = cap;
+  e.ess_win = h->d_esswin;
+  long long it = 0;
+  CK(cudaMemcpyAsync(&it, e.iter, sizeof(it), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const long long win[4] = {it + 1, ndraws, L, cap};
+  CK(cudaMemcpyAsync(h->d_esswin, win, sizeof(win), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t acov_need = (size_t)(L + 1) * P;
+  if (acov_need > h->acov_cap) {
+    void* pnew = nullptr;
+    release_alloc(h, h->d_acov);
+    h->d_acov = nullptr; h->acov_cap = 0;
+    int r = raw_alloc(h, &pnew, acov_need * sizeof(double));
+    if (r) return r;
+    h->d_acov = (double*)pnew;
+    h->acov_cap = acov_need;
+  }
+  if (!h->d_cmean) DA(h->d_cmean, C * P);
+  h->ess_stream_N = ndraws;
+  h->ess_lag = -1;
+  return BNR_OK;
+}
+
+extern "C" int bnr_ess_stream_finish(bnr_handle* h) {
+  if (!h) return fail(BNR_EINVAL, "null handle");
+  if (h->ess_stream_N <= 0 || !h->e.ess_ring) return fail(BNR_ESTATE, "call bnr_ess_stream_begin first");
+  CK(cudaSetDevice(h->p.device));
+  CK(cudaStreamSynchronize(h->stream));
+  long long it = 0, win[4];
+  CK(cudaMemcpy(&it, h->e.iter, sizeof(it), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(win, h->d_esswin, sizeof(win), cudaMemcpyDeviceToHost));
+  if (it < win[0] + win[1] - 1)
+    return fail(BNR_ESTATE, "the streaming window is not complete yet (run the remaining sweeps first)");
+  launch_ess_stream_finalize(h->e, h->ess_stream_N, h->d_acov, h->d_cmean, h->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  h->ess_lag = h->e.ess_L;
+  h->ess_rows = h->ess_stream_N;
+  h->ess_stream_N = 0;
+  drop_graph(h);                         // later sweeps run without the accumulation kernel
+  h->e.ess_ring = h->e.ess_head = h->e.ess_acc = h->e.ess_sum = nullptr;
+  // (the buffer stays with the handle and is reused by the next bnr_ess_stream_begin)
   return BNR_OK;
 }
 
@@ -1206,23 +1350,32 @@ extern "C" int bnr_export_ess(bnr_handle* h, double* dev_acov_dst, double* dev_m
   return BNR_OK;
 }
 
-extern "C" int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts,
-                                  const double* dev_chain_means, int32_t total_chains, int32_t V, int32_t q,
-                                  int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma) {
+extern "C" int bnr_ess_from_stats_lags(int device, const double* dev_acov_parts, int32_t nparts,
+                                       const double* dev_chain_means, int32_t total_chains, int32_t V, int32_t q,
+                                       int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma,
+                                       double* lags_xi, double* lags_gamma) {
   if (!dev_acov_parts || !dev_chain_means || nparts < 1 || total_chains < 1 || nrows < 4 || max_lag < 1)
     return fail(BNR_EINVAL, "bad arguments");
   CK(cudaSetDevice(device));
   const int P = V + q;
-  double* d_out = nullptr;
-  CK(cudaMalloc((void**)&d_out, sizeof(double) * P));
-  launch_ess_finish(dev_acov_parts, nparts, dev_chain_means, total_chains, P, nrows, max_lag, d_out, nullptr, 0);
-  std::vector<double> host(P);
-  cudaError_t err = cudaMemcpy(host.data(), d_out, sizeof(double) * P, cudaMemcpyDeviceToHost);
-  cudaFree(d_out);
-  CK(err);
+  Scratch sc(device, sizeof(double) * 2 * P);
+  if (!sc.p) return fail(BNR_ENOMEM, "device scratch allocation failed");
+  double* d_out = (double*)sc.p;
+  launch_ess_finish(dev_acov_parts, nparts, dev_chain_means, total_chains, P, nrows, max_lag, d_out, d_out + P, 0);
+  std::vector<double> host((size_t)2 * P);
+  CK(cudaMemcpy(host.data(), d_out, sizeof(double) * 2 * P, cudaMemcpyDeviceToHost));
   if (ess_xi) memcpy(ess_xi, host.data(), sizeof(double) * V);
   if (ess_gamma) memcpy(ess_gamma, host.data() + V, sizeof(double) * q);
+  if (lags_xi) memcpy(lags_xi, host.data() + P, sizeof(double) * V);
+  if (lags_gamma) memcpy(lags_gamma, host.data() + P + V, sizeof(double) * q);
   return BNR_OK;
+}
+
+extern "C" int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts,
+                                  const double* dev_chain_means, int32_t total_chains, int32_t V, int32_t q,
+                                  int64_t nrows, int32_t max_lag, double* ess_xi, double* ess_gamma) {
+  return bnr_ess_from_stats_lags(device, dev_acov_parts, nparts, dev_chain_means, total_chains, V, q, nrows, max_lag,
+                                 ess_xi, ess_gamma, nullptr, nullptr);
 }
 
 extern "C" int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag, double* ess_xi,
@@ -1236,6 +1389,12 @@ extern "C" int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t 
 extern "C" int bnr_gamma_mode(bnr_handle* h, int32_t* mode) {
   if (!h || !mode) return fail(BNR_EINVAL, "null argument");
   *mode = h->e.d.gmode;
+  return BNR_OK;
+}
+
+extern "C" int bnr_chain_groups(bnr_handle* h, int32_t* groups) {
+  if (!h || !groups) return fail(BNR_EINVAL, "null argument");
+  *groups = h->n_groups;
   return BNR_OK;
 }
 
@@ -1303,6 +1462,7 @@ extern "C" int bnr_profile_sweep(bnr_handle* h, float* ms) {
   launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
                        (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
   launch_record(e, 1, s);
+  if (e.ess_ring) launch_ess_stream(e, s);
   launch_advance(e, 1, s);
   CK(cudaEventRecord(ev[8], s));
   CK(cudaStreamSynchronize(s));

@@ -210,6 +210,104 @@ __global__ void k_ess_finish(const double* __restrict__ acov_parts, int nparts, 
   if (lag_used) lag_used[p] = (double)t;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Streaming ESS statistics: the same (acov, chain means) as k_chain_mean + k_acov_sum, accumulated while the chains
+// run, so that no chain needs a trace (64 chains x 20 000 draws x 5150 parameters would be 53 GB of traces).
+// Per chain and parameter, with x_0 the first retained draw and y_t = x_t - x_0 (centring on a value of the chain
+// itself keeps the raw lagged products well conditioned):
+//     A_l = sum_{t >= l} y_t y_(t-l)  (l = 0..L),   S = sum_t y_t,   the first L draws (head) and the last L + ES_B (ring)
+// and, at the end, with m = S / N, H_l = sum_{t < l} y_t, T_l = sum_{t >= N-l} y_t:
+//     sum_{t >= l} (y_t - m)(y_(t-l) - m) = A_l - m (2 S - H_l - T_l) + (N - l) m^2 .
+// k_ess_stream runs once per sweep (thread per (chain, parameter)): it appends the draw to the ring and, every ES_B
+// draws (and at the last draw), adds the block's lagged products with a sliding ES_B-wide register window: one ring
+// load and one read-modify-write of A_l per lag and per ES_B draws, i.e. 1/ES_B of the naive per-sweep traffic.
+// grid = (ceil(P/128), C), block = 128.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ES_B = 8;
+
+__global__ void __launch_bounds__(128) k_ess_stream(Engine e) {
+  const Dims& d = e.d;
+  const int P = d.V + d.q;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (p >= P) return;
+  const long long first = e.ess_win[0], N = e.ess_win[1];
+  const int L = (int)e.ess_win[2], cap = (int)e.ess_win[3];
+  const long long k = (*e.iter + 1) - first;        // index of this sweep's draw inside the window
+  if (k < 0 || k >= N) return;
+  const double x = (p < d.V) ? e.xi[c * d.V + p] : e.gamma[(size_t)c * d.qp + (p - d.V)];
+  double* sum = e.ess_sum + (size_t)c * 2 * P;
+  double* ring = e.ess_ring + (size_t)c * cap * P + p;
+  double ref, S;
+  if (k == 0) { ref = x; S = 0.0; sum[p] = ref; }
+  else { ref = sum[p]; S = sum[P + p]; }
+  const double y = x - ref;
+  sum[P + p] = S + y;
+  ring[(size_t)(k % cap) * P] = y;
+  if (k < L) e.ess_head[((size_t)c * L + k) * P + p] = y;
+  const int b = (int)(k % ES_B) + 1;
+  if (b != ES_B && k != N - 1) return;
+  // block of the b newest draws k0 .. k: A_l += sum_j y_(k0+j) y_(k0+j-l)
+  const long long k0 = k - b + 1;
+  double Y[ES_B], w[ES_B];
+#pragma unroll
+  for (int j = 0; j < ES_B; ++j) {
+    Y[j] = (j < b) ? ring[(size_t)((k0 + j) % cap) * P] : 0.0;
+    w[j] = Y[j];
+  }
+  double* A = e.ess_acc + (size_t)c * (L + 1) * P + p;
+  const int lmax = (long long)L < k ? L : (int)k;
+  const bool fresh = (k0 == 0);                     // first block of the window: A starts from zero
+  for (int l = 0; l <= L; ++l) {
+    if (l > 0) {
+#pragma unroll
+      for (int j = ES_B - 1; j > 0; --j) w[j] = w[j - 1];
+      w[0] = (k0 - l >= 0) ? ring[(size_t)((k0 - l) % cap) * P] : 0.0;
+    }
+    if (l > lmax) { if (fresh) A[(size_t)l * P] = 0.0; continue; }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < ES_B; ++j) s += Y[j] * ((k0 + j - l >= 0) ? w[j] : 0.0);
+    A[(size_t)l * P] = (fresh ? 0.0 : A[(size_t)l * P]) + s;
+  }
+}
+
+// acov[l][p] = sum_c (1/N) sum_{t >= l} (x_t - mean_c)(x_(t-l) - mean_c), cmean[c][p]; thread per parameter, chains in
+// a fixed order (deterministic).  grid = ceil(P/128), block = 128.
+__global__ void __launch_bounds__(128) k_ess_stream_finalize(Engine e, long long N, double* __restrict__ acov,
+                                                             double* __restrict__ cmean) {
+  const Dims& d = e.d;
+  const int P = d.V + d.q, L = e.ess_L, cap = e.ess_cap;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double n = (double)N;
+  for (int c = 0; c < d.C; ++c) {
+    const double ref = e.ess_sum[(size_t)c * 2 * P + p], S = e.ess_sum[(size_t)c * 2 * P + P + p];
+    const double m = S / n;
+    cmean[(size_t)c * P + p] = ref + m;
+    const double* A = e.ess_acc + (size_t)c * (L + 1) * P + p;
+    const double* head = e.ess_head + (size_t)c * L * P + p;
+    const double* ring = e.ess_ring + (size_t)c * cap * P + p;
+    double H = 0.0, T = 0.0;
+    for (int l = 0; l <= L; ++l) {
+      if (l >= 1) {
+        H += head[(size_t)(l - 1) * P];
+        T += ring[(size_t)((N - l) % cap) * P];
+      }
+      const double v = (A[(size_t)l * P] - m * (2.0 * S - H - T) + (n - l) * m * m) / n;
+      acov[(size_t)l * P + p] = (c == 0 ? 0.0 : acov[(size_t)l * P + p]) + v;
+    }
+  }
+}
+
+void launch_ess_stream(const Engine& e, cudaStream_t s) {
+  dim3 grid((e.d.V + e.d.q + 127) / 128, e.d.C);
+  ++g_launches; k_ess_stream<<<grid, 128, 0, s>>>(e);
+}
+
+void launch_ess_stream_finalize(const Engine& e, long long N, double* acov, double* cmean, cudaStream_t s) {
+  ++g_launches; k_ess_stream_finalize<<<(e.d.V + e.d.q + 127) / 128, 128, 0, s>>>(e, N, acov, cmean);
+}
+
 void launch_chain_mean(const double* tr, long long trace_rows, int P, int C, long long first, long long N,
                        double* cmean, cudaStream_t s) {
   dim3 grid((P + 127) / 128, C);

@@ -9,6 +9,7 @@ namespace bnr {
 constexpr int MAX_R = 16;
 constexpr int TILE_N = 128;   // n is padded to a multiple of this (SYRK / Cholesky tiles)
 constexpr int TILE_K = 16;    // q is padded to a multiple of this (SYRK k-step)
+constexpr int TAU2_MAX_BLOCKS = 32;   // blocks per chain of the tau2 reduction
 constexpr int PART_BLOCK = 256;  // threads per block of the edge kernels (partials granularity)
 
 struct Dims {
@@ -19,6 +20,7 @@ struct Dims {
                       // > n resp. q: the first padding row carries the right-hand side of the forward solve
   int nparts;         // edge-kernel blocks per chain = ceil(q / PART_BLOCK)
   int chain_offset;
+  int chain_offset_local;   // index of this view's first chain inside the handle (0 for the handle itself)
   int gigK;           // injected uniforms per edge
   uint64_t seed;
   double eta, zeta, iota, a_delta, b_delta, nu;
@@ -106,6 +108,8 @@ struct Engine {
   int syrk_ws_cap;  // splits - 1, fixed per handle
   double* Linv;     // [C][gdim/128][128*128]  inverses of the 128 x 128 diagonal blocks of the factor (column-major)
   double* partials; // [C][nparts][2*MAX_R+1]  block partial sums: A_r, B_r (lambda), sum S
+  double* tau2_part;      // [handle chains][2 * TAU2_MAX_BLOCKS] partial sums of the tau2 reduction (NOT offset per view)
+  unsigned* tau2_ticket;  // [handle chains] arrival counters of its blocks
   int* status;      // [C]
   long long* iter;  // device scalar: completed sweeps
   long long* trace_row;   // device scalar: next trace row
@@ -114,6 +118,13 @@ struct Engine {
   long long* mom_window;  // device [5]: split-half window (first sweep, len), block moments (first sweep, block len, blocks)
   double* bmom;           // [C][bmom_nb][V+q][2] per-block (mean, M2): mergeable R-hat windows (doubling scheme)
   int bmom_nb;
+  // streaming ESS statistics (bnr_ess_stream_begin; kernels in bnr_diagnostics.cu).  y_t = x_t - x_first per chain / parameter
+  double* ess_ring;       // [C][ess_cap][V+q]  ring of the last ess_cap centred draws
+  double* ess_head;       // [C][L][V+q]        the first L centred draws
+  double* ess_acc;        // [C][L+1][V+q]      lagged products A_l = sum_t y_t y_(t-l)
+  double* ess_sum;        // [C][2][V+q]        x_first, sum_t y_t
+  const long long* ess_win;  // device [4]: first sweep, draws N, max lag L, ring capacity ess_cap
+  int ess_L, ess_cap;
   // traces
   int trace_full_chains; int trace_gx_chains; long long trace_rows;   // leading chains with full / (xi, gamma) rows
   double* tr_full;  // [trace_full_chains][rows][rowlen_full]

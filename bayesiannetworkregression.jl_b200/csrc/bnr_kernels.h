@@ -45,8 +45,12 @@ int syrk_splits(const Dims& d, int C);                        // k-splits launch
 // optional second stream + events that let launch_cholesky run the off-diagonal panel updates next to the panel
 // factorisation (works eagerly and under stream capture, where it becomes a fork/join of the graph)
 struct ForkJoin {
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr;   // low priority: throughput work (the Gram SYRK)
+  cudaStream_t side_hi = nullptr;// same priority as the main stream: the Cholesky's look-ahead branch (it feeds the
+                                 // critical path two steps later and must not queue behind other groups' SYRK CTAs)
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t* pool = nullptr;   // 4 events per Cholesky panel (see launch_cholesky); owned by the handle
+  int npool = 0;
 };
 // in-place lower Cholesky of every G_c (gdim x gdim); the forward solve L w = rhs rides along as a bordering row
 void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStream_t s);
@@ -66,6 +70,10 @@ void launch_chain_mean(const double* tr, long long trace_rows, int P, int C, lon
                        double* cmean, cudaStream_t s);
 void launch_acov_sum(const double* tr, long long trace_rows, int P, int C, long long first, long long N, int L,
                      const double* cmean, double* acov, cudaStream_t s);
+// streaming ESS: per-sweep lagged-product accumulation (no all-chain trace) and its conversion into the statistics
+// launch_acov_sum / launch_chain_mean produce (acov [L+1][P] summed over the local chains, chain means [C][P])
+void launch_ess_stream(const Engine& e, cudaStream_t s);
+void launch_ess_stream_finalize(const Engine& e, long long N, double* acov, double* cmean, cudaStream_t s);
 void launch_ess_finish(const double* acov_parts, int nparts, const double* cmeans, int chains, int P, long long N,
                        int L, double* ess, double* lag_used, cudaStream_t s);
 

@@ -5,6 +5,7 @@
 //   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
 //   X v, X' a4 (all chains at once)   -> k_xmma (tall-skinny DMMA GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
+#include <cstdlib>
 #include "bnr_engine.cuh"
 #include "bnr_kernels.h"
 
@@ -291,18 +292,11 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     } else {
       ib = jb = t - noff;
     }
-  } else if (MODE == 1) {
-    // left-looking update of block column J = origin: tiles (J+1 .. T-1, J) first, the diagonal tile (J, J) last
-    // part 1: the diagonal tile alone, part 2: the tiles below it (the two halves can run concurrently)
-    const int T = np / SY_BT, nt = T - origin;
-    jb = origin;
-    if (part == 1) ib = origin;
-    else if (part == 2) ib = origin + 1 + blockIdx.y;
-    else ib = (blockIdx.y == nt - 1) ? origin : origin + 1 + blockIdx.y;
   } else {
-    // MODE 2: panel solve, tiles (J+1 .. T-1, J)
+    // MODE 1 (Cholesky update of block column jb = origin) and MODE 2 (panel solve of block column jb): the CTAs of a
+    // launch cover the row blocks part, part + 1, ... of that column (part >= jb; part == jb includes the diagonal tile)
     jb = origin;
-    ib = origin + 1 + blockIdx.y;
+    ib = part + blockIdx.y;
   }
   const int i0 = ib * SY_BT, j0 = jb * SY_BT;
   const bool diag = (ib == jb);
@@ -409,17 +403,16 @@ k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ sca
   }
 }
 
-// G_c (lower tiles) += sum_z ws[c][z].  grid = (lower tiles, C), block = 256
+// G_c (lower tiles) += sum_z ws[c][z] (fixed order).  grid = (lower tiles * 8, C), block = 256: 2048 entries per block
 __global__ void __launch_bounds__(256) k_syrk_splitk_reduce(double* __restrict__ G, size_t g_chain_stride, int np,
                                                             const double* __restrict__ ws, int ws_cap, int nz) {
-  const int T = np / SY_BT, c = blockIdx.y;
-  int t = blockIdx.x, ib = 0;
+  const int c = blockIdx.y, piece = blockIdx.x & 7;
+  int t = blockIdx.x >> 3, ib = 0;
   while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
   const int jb = t - ib * (ib + 1) / 2;
-  (void)T;
   double* Gc = G + (size_t)c * g_chain_stride;
   const double* wc = ws + (size_t)c * ws_cap * g_chain_stride;
-  for (int id = threadIdx.x; id < SY_BT * SY_BT; id += 256) {
+  for (int id = piece * 2048 + threadIdx.x; id < (piece + 1) * 2048; id += 256) {
     const int i = ib * SY_BT + (id & (SY_BT - 1)), j = jb * SY_BT + (id >> 7);
     const size_t o = (size_t)j * np + i;
     double v = Gc[o];
@@ -428,19 +421,22 @@ __global__ void __launch_bounds__(256) k_syrk_splitk_reduce(double* __restrict__
   }
 }
 
+// G[ib, jb] -= sum_k P[ib, k] P[jb, k]' for the row blocks ib = ib_first, ib_first + 1, ... (grid.y of them) of block
+// column jb; P points at the first of the nk * 16 columns of the factor that contribute (the caller offsets it), so a
+// launch applies any contiguous range of panels.
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
-              int nk, int origin, int part) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, origin, 0.0, nullptr, 0, part);
+              int nk, int jb, int ib_first) {
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, nullptr, 0, ib_first);
 }
 
-// panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I > J (in place: a CTA has consumed
-// its whole tile through the ring before the first store)
+// panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I = ib_first, ... (in place: a CTA
+// has consumed its whole tile through the ring before the first store)
 __global__ void __launch_bounds__(SY_THREADS, 1)
-k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int origin,
+k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int jb, int ib_first,
             const double* __restrict__ Linv, size_t linv_chain_stride) {
-  syrk_body<2>(G, chain_stride, np, nullptr, 0, G, chain_stride, np, nvalid, SY_BT / SY_BK, origin, 0.0, Linv,
-               linv_chain_stride);
+  syrk_body<2>(G, chain_stride, np, nullptr, 0, G, chain_stride, np, nvalid, SY_BT / SY_BK, jb, 0.0, Linv,
+               linv_chain_stride, ib_first);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -524,30 +520,121 @@ __device__ __forceinline__ void frag_mm32(double& c0, double& c1, const double* 
 constexpr int PLD = 132;           // column stride of the 128 x 128 working block (== 4 mod 16: conflict-free fragments)
 constexpr int XD_LD = 36;          // column stride of the 32 x 32 scratch blocks (== 4 mod 16)
 constexpr int XD_BLK = 32 * XD_LD;
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB + 64) + 16;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB + 64) + 32;
+constexpr int PU_ROWS = 32;        // k-rows of L(J, J-1) per staged chunk of the in-kernel diagonal update
+static_assert(2 * PU_ROWS * PLD <= 8 * XD_BLK, "the update ring aliases the inverse scratch");
 
+// One 32-k-row chunk of the diagonal-block update Delta += Lp Lp' (lower triangle by 8 x 8 fragments): warp W owns the
+// fragment columns W and 15 - W (17 fragments, the same count for every warp) exactly like syrk_diag_tile.
+template <int W>
+__device__ __forceinline__ void potf2_update_chunk(const double* buf, int lk, int lr, double (&acc)[17][2]) {
+  constexpr int NA = 16 - W;
+#pragma unroll
+  for (int k4 = 0; k4 < PU_ROWS / 4; ++k4) {
+    const double* row = buf + (k4 * 4 + lk) * PLD + lr;
+    const double a0 = row[W * 8], a1 = row[(15 - W) * 8];
+    double bfr[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) bfr[i] = row[(W + i) * 8];
+#pragma unroll
+    for (int t = 0; t < NA; ++t) dmma884(acc[t][0], acc[t][1], a0, bfr[t]);
+#pragma unroll
+    for (int t = NA; t < 17; ++t) dmma884(acc[t][0], acc[t][1], a1, bfr[t - 1 - W]);
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void potf2_update_apply(double* A, int lk, int lr, const double (&acc)[17][2]) {
+  constexpr int NA = 16 - W;
+#pragma unroll
+  for (int t = 0; t < 17; ++t) {
+    const int jf = (t < NA) ? W : 15 - W;
+    const int ifr = (t < NA) ? W + t : t - 1;
+    double2* p = reinterpret_cast<double2*>(A + (jf * 8 + lr) * PLD + ifr * 8 + 2 * lk);
+    double2 v = *p;
+    v.x -= acc[t][0];
+    v.y -= acc[t][1];
+    *p = v;
+  }
+}
+
+// Panel kernel of the blocked Cholesky, one CTA per chain:
+//   (late update)  D = G[J, J] - L[J, J-1] L[J, J-1]'   when `late` (the contributions of the panels before J-1 were
+//                  applied earlier by k_chol_update; L[J, J-1] streams through a two-buffer TMA ring into DMMA fragments)
+//   (factor)       D = L_JJ L_JJ'                       in shared memory, 32-wide steps
+//   (inverse)      Linv_J = L_JJ^-1                     in place, 32^3 DMMA block products
 __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_t chain_stride, int N, int J,
-                                                   double* __restrict__ Linv, int T, int* status) {
+                                                   double* __restrict__ Linv, int T, int* status, int late) {
   extern __shared__ __align__(16) double sm[];
   double* A = sm;                          // column-major 128 x 128 working block: A[col * PLD + row]
   double* Xd = sm + PB * PLD;              // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
   double* Tm = Xd + 4 * XD_BLK;            // [4] intermediate products of the inverse
   double* dall = Tm + 4 * XD_BLK;          // [128] reciprocal diagonal of L
   double* Lcol = dall + PB;                // [2][32] current column of the 32 x 32 factorisation (double-buffered)
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);   // [0] block load, [1..2] update ring
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lk = lane & 3, lr = lane >> 2;
-  double* D = G + (size_t)c * chain_stride + (size_t)J * PB * N + (size_t)J * PB;
+  double* Gc = G + (size_t)c * chain_stride;
+  double* D = Gc + (size_t)J * PB * N + (size_t)J * PB;
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, PB * PB * 8);
-    for (int col = 0; col < PB; ++col) bulk_g2s(A + col * PLD, D + (size_t)col * N, PB * 8, bar);
+  if (warp == 0) {
+    if (lane == 0) mbar_expect_tx(&bar[0], PB * PB * 8);
+    __syncwarp();
+#pragma unroll
+    for (int col = lane; col < PB; col += 32) bulk_g2s(A + col * PLD, D + (size_t)col * N, PB * 8, &bar[0]);
   }
-  mbar_wait(bar, 0);
+  if (late && J > 0) {
+    // L[J, J-1]: rows J*128.., columns (J-1)*128..: element (row, k) at Lp[row + N * k]
+    const double* Lp = Gc + (size_t)(J - 1) * PB * N + (size_t)J * PB;
+    double* ring = Xd;
+    auto issue = [&](int chunk) {            // by warp 1: lane l loads k-row chunk * 32 + l
+      double* buf = ring + (chunk & 1) * PU_ROWS * PLD;
+      if (lane == 0) mbar_expect_tx(&bar[1 + (chunk & 1)], PU_ROWS * PB * 8);
+      __syncwarp();
+      bulk_g2s(buf + lane * PLD, Lp + (size_t)(chunk * PU_ROWS + lane) * N, PB * 8, &bar[1 + (chunk & 1)]);
+    };
+    if (warp == 1) { issue(0); issue(1); }
+    double acc[17][2];
+#pragma unroll
+    for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+    constexpr int NCH = PB / PU_ROWS;
+    for (int chunk = 0; chunk < NCH; ++chunk) {
+      mbar_wait(&bar[1 + (chunk & 1)], (chunk >> 1) & 1);
+      const double* buf = ring + (chunk & 1) * PU_ROWS * PLD;
+      switch (warp) {
+        case 0: potf2_update_chunk<0>(buf, lk, lr, acc); break;
+        case 1: potf2_update_chunk<1>(buf, lk, lr, acc); break;
+        case 2: potf2_update_chunk<2>(buf, lk, lr, acc); break;
+        case 3: potf2_update_chunk<3>(buf, lk, lr, acc); break;
+        case 4: potf2_update_chunk<4>(buf, lk, lr, acc); break;
+        case 5: potf2_update_chunk<5>(buf, lk, lr, acc); break;
+        case 6: potf2_update_chunk<6>(buf, lk, lr, acc); break;
+        default: potf2_update_chunk<7>(buf, lk, lr, acc); break;
+      }
+      if (chunk + 2 < NCH) {
+        __syncthreads();                     // every warp is done with this buffer before the TMA engine refills it
+        if (warp == 1) issue(chunk + 2);
+      }
+    }
+    mbar_wait(&bar[0], 0);
+    switch (warp) {
+      case 0: potf2_update_apply<0>(A, lk, lr, acc); break;
+      case 1: potf2_update_apply<1>(A, lk, lr, acc); break;
+      case 2: potf2_update_apply<2>(A, lk, lr, acc); break;
+      case 3: potf2_update_apply<3>(A, lk, lr, acc); break;
+      case 4: potf2_update_apply<4>(A, lk, lr, acc); break;
+      case 5: potf2_update_apply<5>(A, lk, lr, acc); break;
+      case 6: potf2_update_apply<6>(A, lk, lr, acc); break;
+      default: potf2_update_apply<7>(A, lk, lr, acc); break;
+    }
+    __syncthreads();
+  } else {
+    mbar_wait(&bar[0], 0);
+  }
   bool bad = false;
   for (int s = 0; s < PB / 32; ++s) {
     const int o = s * 32;
@@ -569,11 +656,14 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
         double* lc = Lcol + (j & 1) * 32;
         lc[lane] = lj;
         if (lane == j) dall[o + j] = inv;
-        __syncwarp();
         if (j + 1 < 32) {
-          a[j + 1] -= lj * lc[j + 1];
+          // next pivot first, without the round trip through shared memory: for the lane that owns row j + 1 the
+          // multiplier lc[j + 1] is its own lj (bit-identical to the generic update below)
+          if (lane == j + 1) a[j + 1] = fma(-lj, lj, a[j + 1]);
           djj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
         }
+        __syncwarp();
+        if (j + 1 < 32 && lane != j + 1) a[j + 1] = fma(-lj, lc[j + 1], a[j + 1]);
 #pragma unroll
         for (int cc = j + 2; cc < 32; ++cc) a[cc] -= lj * lc[cc];
       }
@@ -628,8 +718,9 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   // the factor goes back to global memory (full columns: the part above the diagonal is never read by anyone)
   fence_async_smem();
   __syncthreads();
-  if (tid == 0) {
-    for (int col = 0; col < PB; ++col) bulk_s2g(D + (size_t)col * N, A + col * PLD, PB * 8);
+  if (warp == 0) {
+#pragma unroll
+    for (int col = lane; col < PB; col += 32) bulk_s2g(D + (size_t)col * N, A + col * PLD, PB * 8);
     bulk_commit();
     bulk_wait_read0();
   }
@@ -712,9 +803,10 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   }
   fence_async_smem();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
     double* dst = Linv + ((size_t)c * T + J) * PB * PB;
-    for (int col = 0; col < PB; ++col) bulk_s2g(dst + col * PB, A + col * PLD, PB * 8);
+#pragma unroll
+    for (int col = lane; col < PB; col += 32) bulk_s2g(dst + col * PB, A + col * PLD, PB * 8);
     bulk_commit();
     bulk_wait0();
   }
@@ -1004,12 +1096,20 @@ void linalg_setup() {
   cudaFuncSetAttribute(k_bwd_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
-// k-splits of the SYRK for a batch of C chains: enough CTAs for ~2 per SM, at least 32 k-steps per split
+// k-splits of the SYRK for a handle of C chains: when chains x tiles is below ~4 waves of CTAs, a CTA (one 128 x 128
+// tile over the whole contraction: 0.7 ms at q = 5050, 2.7 ms at q = 20100) is too coarse a unit of work to balance over
+// 148 SMs, so the contraction is cut into up to 8 pieces of at least 24 k-steps.  The count depends on the handle's chain
+// count only (not on the chain groups, which each launch a part of the chains).
 int syrk_splits(const Dims& d, int C) {
   const int T = d.np / SY_BT, tiles = T * (T + 1) / 2, nk = d.qp / SY_BK;
-  if (tiles * C >= 148) return 1;
-  int s = (2 * 148 + tiles * C - 1) / (tiles * C);
-  if (s > nk / 32) s = nk / 32;
+  if (const char* ov = getenv("BNR_SYRK_SPLITS")) {                       // tuning knob
+    int s = atoi(ov);
+    if (s > nk / 8) s = nk / 8;
+    return s < 1 ? 1 : (s > SYRK_MAX_SPLITS ? SYRK_MAX_SPLITS : s);
+  }
+  if (tiles * C >= 4 * 148) return 1;
+  int s = (4 * 148 + tiles * C - 1) / (tiles * C);
+  if (s > nk / 24) s = nk / 24;
   if (s > SYRK_MAX_SPLITS) s = SYRK_MAX_SPLITS;
   return s < 1 ? 1 : s;
 }
@@ -1031,7 +1131,7 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
   ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, gs, d.np, d.n, nk, 1.0,
                                                             nk_split, e.syrk_ws, e.syrk_ws_cap);
   if (ns > 1) {
-    dim3 g2(T * (T + 1) / 2, d.C);
+    dim3 g2(T * (T + 1) / 2 * 8, d.C);
     ++g_launches; k_syrk_splitk_reduce<<<g2, 256, 0, s>>>(e.G, gs, d.np, e.syrk_ws, e.syrk_ws_cap, ns - 1);
   }
   if (e.aux.G_copy) {
@@ -1086,40 +1186,58 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
   }
 }
 
-// factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix.
-// Per panel J the critical chain is  diagonal-tile update -> k_potf2_inv -> panel solve; the update of the tiles
-// below the diagonal depends only on the previous panel, so it runs on `side` (a forked branch of the graph) while
-// the latency-bound, one-CTA-per-chain panel factorisation occupies at most C SMs.
+// Factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix.
+// Schedule: left-looking with a one-panel lookahead, so that the latency-bound chain is as short as it can be with one
+// kernel per step.  Per panel J, in program order (every tile sees its updates in this order on any schedule):
+//   PA(J)      k_potf2_inv    D_JJ -= L[J,J-1] L[J,J-1]' (late part, in the kernel), factor, invert       [main]
+//   T1(J)      k_trsm_dmma    tile (J+1, J)                                                               [main]
+//   T2(J)      k_trsm_dmma    tiles (i, J), i >= J+2                                                      [side]
+//   Ulate(J)   k_chol_update  tiles (i, J+1), i >= J+2, contribution of panel J only (depth 128)          [side]
+//   Uearly(J)  k_chol_update  tiles (i, J+2), i >= J+2 (diagonal included), panels 0..J (depth 128 (J+1)) [side]
+// i.e. block column j receives the panels 0..j-2 early (as soon as they exist, off the critical path) and panel j-1
+// late.  The critical path per panel is PA + T1; everything else runs on `side` (a forked branch of the graph) next to
+// the following panel factorisation, which occupies at most one SM per chain.
+//   dependencies across the two streams:  T2(J) after PA(J);  Ulate(J) after T1(J);
+//                                         T1(J+1) after Ulate(J);  PA(J+2) after Uearly(J).
+// Without a side stream the same kernels run in program order on `s` (identical results).
 void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
   const int m = d.gmode == 2 ? d.q : d.n;         // first padding row = the bordering row
   const size_t cs = (size_t)N * N;
   const int T = N / PB;
+  const size_t ls = (size_t)T * PB * PB;
+  static const bool serial = getenv("BNR_CHOL_SERIAL") != nullptr;        // debugging knob: program order on one stream
+  const bool fork = !serial && fj.side_hi != nullptr && fj.pool != nullptr && fj.npool >= 4 * T;
+  cudaStream_t side = fork ? fj.side_hi : s;
+  cudaEvent_t* evP = fj.pool;                       // [T] each: after PA, after T1, after Ulate, after Uearly
+  cudaEvent_t* evT = fj.pool + T;
+  cudaEvent_t* evL = fj.pool + 2 * T;
+  cudaEvent_t* evE = fj.pool + 3 * T;
   ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
   for (int J = 0; J < T; ++J) {
-    const bool fork = fj.side != nullptr && J > 0 && J + 1 < T;
-    if (J > 0) {
-      const int nk = J * PB / SY_BK;
-      if (fork) {
-        cudaEventRecord(fj.fork, s);
-        cudaStreamWaitEvent(fj.side, fj.fork, 0);
-        dim3 g2(d.C, T - J - 1);
-        ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, fj.side>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 2);
-        cudaEventRecord(fj.join, fj.side);
-        dim3 g1(d.C, 1);
-        ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 1);
-      } else {
-        dim3 g2(d.C, T - J);
-        ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, 0);
-      }
-    }
-    ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status);
-    if (fork) cudaStreamWaitEvent(s, fj.join, 0);
+    const bool has_side = J + 2 < T;
+    if (fork && J >= 2) cudaStreamWaitEvent(s, evE[J - 2], 0);
+    ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status, J > 0 ? 1 : 0);
+    if (fork && has_side) cudaEventRecord(evP[J], s);
     if (J + 1 < T) {
-      dim3 g1(d.C, T - J - 1);
-      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, e.Linv + (size_t)J * PB * PB,
-                                                              (size_t)T * PB * PB);
+      if (fork && J >= 1 && J + 1 < T) cudaStreamWaitEvent(s, evL[J - 1], 0);
+      dim3 g1(d.C, 1);
+      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls);
+      if (fork && has_side) cudaEventRecord(evT[J], s);
+    }
+    if (has_side) {
+      const int rows = T - J - 2;                   // row blocks J+2 .. T-1
+      if (fork) cudaStreamWaitEvent(side, evP[J], 0);
+      dim3 g2(d.C, rows);
+      ++g_launches; k_trsm_dmma<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, m + 1, J, J + 2, e.Linv + (size_t)J * PB * PB, ls);
+      if (fork) cudaStreamWaitEvent(side, evT[J], 0);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1,
+                                                                   PB / SY_BK, J + 1, J + 2);
+      if (fork) cudaEventRecord(evL[J], side);
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, e.G, N, m + 1, (J + 1) * PB / SY_BK,
+                                                                   J + 2, J + 2);
+      if (fork) cudaEventRecord(evE[J], side);
     }
   }
 }

@@ -68,12 +68,14 @@ __device__ bool warp_chol(double* A, int R, int lane) {
 
 // ------------------------------------------------------------------------------------------------------------
 // tau^2  (update_tau2!, src/gibbs.jl:267-277): InverseGamma(n/2 + q/2, 1/2 |y - mu - X gamma|^2 + 1/2 sum (gamma-W)^2/S)
-// grid = C, block = 256.  X gamma comes from the cache e.xg.
+// grid = (nb, C), block = 256: the two sums are split over nb = tau2_blocks(q) blocks per chain; the last block to
+// finish (ticket counter) adds the partial sums in block order -- deterministic -- and draws.  X gamma comes from e.xg.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_tau2(Engine e) {
   extern __shared__ double sm[];
+  __shared__ unsigned ticket;
   const Dims& d = e.d;
-  const int c = blockIdx.x, tid = threadIdx.x;
+  const int c = blockIdx.y, tid = threadIdx.x, nb = gridDim.x, b = blockIdx.x;
   double* us = sm;                 // [V*R]
   double* lam = us + d.V * d.R;    // [R]
   double* red = lam + d.R;         // [32]
@@ -82,12 +84,12 @@ __global__ void __launch_bounds__(256) k_tau2(Engine e) {
   __syncthreads();
   const double mu = e.mu[c];
   double s1 = 0.0;
-  for (int i = tid; i < d.n; i += blockDim.x) {
+  for (int i = b * blockDim.x + tid; i < d.n; i += nb * blockDim.x) {
     const double r = e.y[i] - mu - e.xg[(size_t)c * d.np + i];
     s1 += r * r;
   }
   double s2 = 0.0;
-  for (int j = tid; j < d.q; j += blockDim.x) {
+  for (int j = b * blockDim.x + tid; j < d.q; j += nb * blockDim.x) {
     const int2 lk = e.edge_lk[j];
     double w = 0.0;
     for (int r = 0; r < d.R; ++r) w += lam[r] * us[lk.y * d.R + r] * us[lk.x * d.R + r];
@@ -96,7 +98,20 @@ __global__ void __launch_bounds__(256) k_tau2(Engine e) {
   }
   s1 = block_sum(s1, red);
   s2 = block_sum(s2, red);
+  double* part = e.tau2_part + (size_t)(d.chain_offset_local + c) * 2 * TAU2_MAX_BLOCKS;
   if (tid == 0) {
+    part[2 * b] = s1; part[2 * b + 1] = s2;
+    __threadfence();
+    ticket = atomicAdd(&e.tau2_ticket[d.chain_offset_local + c], 1u);
+  }
+  __syncthreads();
+  if (ticket != (unsigned)(nb - 1)) return;
+  if (tid == 0) {
+    __threadfence();
+    e.tau2_ticket[d.chain_offset_local + c] = 0u;      // ready for the next sweep
+    const volatile double* vp = part;
+    s1 = 0.0; s2 = 0.0;
+    for (int k = 0; k < nb; ++k) { s1 += vp[2 * k]; s2 += vp[2 * k + 1]; }
     const long long it = *e.iter + 1;
     const double shape = 0.5 * d.n + 0.25 * (double)d.V * (d.V + 1);
     const double scale = 0.5 * s1 + s2;
@@ -410,10 +425,13 @@ __global__ void __launch_bounds__(PART_BLOCK) k_gamma_gig(Engine e, int flags) {
 //   theta (476-479), Delta (496-499 + sample_Beta 130-140), M (516-547), mu (565-570), lambda (586-613), pi (630-636)
 // grid = C, block = 256.
 // ------------------------------------------------------------------------------------------------------------
+// The draws of the different conditionals are independent streams, so they run CONCURRENTLY on different warps
+// (warp 1: theta, 2: Delta, 3: mu, 4..: the Bartlett variates of M, one stream per variate; 7: lambda / pi per r);
+// warp 0 then does the R x R linear algebra of M.  A single sequential thread used to take ~40 us here.
 __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
   extern __shared__ double sm[];
   const Dims& d = e.d;
-  const int c = blockIdx.x, tid = threadIdx.x, R = d.R, V = d.V, RR = R * R;
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, R = d.R, V = d.V, RR = R * R;
   double* us = sm;                 // [V*R]
   double* psi = us + V * R;        // [4 * RR]: Psi, chol(Psi), Bartlett factor, Y (M update)
   double* sums = psi + 4 * RR;     // [2*MAX_R+1]
@@ -422,6 +440,9 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
   const InjLayout L = InjLayout::make(d.n, V, R, d.gigK);
   const double* injc = e.inj ? e.inj + (size_t)c * e.inj_stride : nullptr;
   const RngKey key = chain_key(d, c);
+  const bool do_theta = mask & (1 << BNR_COND_THETA_), do_delta = mask & (1 << BNR_COND_DELTA_);
+  const bool do_M = mask & (1 << BNR_COND_M_), do_mu = mask & (1 << BNR_COND_MU_);
+  const bool do_lam = mask & (1 << BNR_COND_LAMBDA_), do_pi = mask & (1 << BNR_COND_PI_);
 
   for (int i = tid; i < V * R; i += blockDim.x) us[i] = e.u[(size_t)c * V * R + i];
   if (tid < 2 * R + 1) {
@@ -429,18 +450,9 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
     for (int p = 0; p < d.nparts; ++p) s += e.partials[((size_t)c * d.nparts + p) * (2 * MAX_R + 1) + tid];
     sums[tid] = s;
   }
-  __syncthreads();
-
-  if ((mask & (1 << BNR_COND_THETA_)) && tid == 0) {
-    const double shape = d.zeta + 0.5 * (double)V * (V + 1);
-    const double scale = 2.0 / (2.0 * d.iota + sums[2 * R]);
-    DrawStream st(key, (uint32_t)it, SITE_THETA, 0, injc ? injc + L.theta : nullptr, 1);
-    e.theta[c] = st.gamma(shape) * scale;
-    if (e.aux.theta_params) { e.aux.theta_params[2 * c] = shape; e.aux.theta_params[2 * c + 1] = scale; }
-  }
-
-  if (mask & ((1 << BNR_COND_DELTA_) | (1 << BNR_COND_M_))) {
-    double sx = 0.0, nz = 0.0;
+  // block reductions first (every thread takes part): sum xi, #{xi != 0}, sum (y - X gamma)
+  double sx = 0.0, nz = 0.0, sy = 0.0;
+  if (do_delta || do_M) {
     for (int k = tid; k < V; k += blockDim.x) {
       const double x = e.xi[c * V + k];
       sx += x;
@@ -448,114 +460,72 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
     }
     sx = block_sum(sx, red);
     nz = block_sum(nz, red);
-    if ((mask & (1 << BNR_COND_DELTA_)) && tid == 0) {
-      const double a = d.a_delta + sx, b = d.b_delta + ((double)V - sx);
-      DrawStream st(key, (uint32_t)it, SITE_DELTA, 0, injc ? injc + L.Delta : nullptr, 3);
-      double dl;
-      if (a > 0.0 && b > 0.0) {
-        const double ga = st.gamma(a), gb = st.gamma(b);
-        dl = ga / (ga + gb);
-      } else if (a > 0.0) dl = 1.0;
-      else if (b > 0.0) dl = 0.0;
-      else {
-        if (injc) { st.pos = 2; }
-        dl = (st.uniform() < 0.5) ? 0.0 : 1.0;
-      }
-      e.Delta[c] = dl;
-      if (e.aux.delta_params) { e.aux.delta_params[2 * c] = a; e.aux.delta_params[2 * c + 1] = b; }
-    }
-    if (mask & (1 << BNR_COND_M_)) {
-      // Psi = I + sum_k u_k u_k'
-      for (int en = tid; en < RR; en += blockDim.x) {
-        const int a = en % R, b = en / R;
-        double s = (a == b) ? 1.0 : 0.0;
-        for (int k = 0; k < V; ++k) s += us[k * R + a] * us[k * R + b];
-        psi[en] = s;
-      }
-      __syncthreads();
-      // The variates come from ONE sequential stream (thread 0, same order as before: R chi-squares, then the
-      // strictly-lower normals row by row); the R x R linear algebra is done by warp 0 in shared memory -- the
-      // single-thread version with its three local-memory R x R arrays was the longest kernel of the small configs.
-      double* Lp = psi + RR;          // chol(Psi), lower
-      double* Ab = Lp + RR;           // Bartlett factor, lower
-      double* Yw = Ab + RR;           // Y = A^-1 Lp'
-      const double df = d.nu + nz;
-      if (tid == 0) {
-        DrawStream st(key, (uint32_t)it, SITE_M, 0, injc ? injc + L.M : nullptr, R + R * (R - 1) / 2);
-        for (int i = 0; i < R; ++i) {
-          const double ci = injc ? st.uniform() : 2.0 * st.gamma(0.5 * (df - i));
-          Ab[i + R * i] = sqrt(ci);
-        }
-        for (int i = 0; i < R; ++i)
-          for (int j = 0; j < i; ++j) Ab[i + R * j] = st.normal();
-      }
-      for (int i = tid; i < RR; i += blockDim.x) Lp[i] = psi[i];
-      __syncthreads();
-      if (tid < 32) {
-        const int lane = tid;
-        // Cholesky of Psi, column by column: lane i owns row i (same summation order as small_chol)
-        bool ok = true;
-        for (int j = 0; j < R; ++j) {
-          double sdot = 0.0;
-          if (lane >= j && lane < R) {
-            sdot = Lp[lane + R * j];
-            for (int p = 0; p < j; ++p) sdot -= Lp[lane + R * p] * Lp[j + R * p];
-          }
-          const double dj = __shfl_sync(0xffffffffu, sdot, j);
-          if (!(dj > 0.0)) ok = false;
-          const double rt = sqrt(dj);
-          if (lane == j) Lp[j + R * j] = rt;
-          else if (lane > j && lane < R) Lp[lane + R * j] = sdot / rt;
-          __syncwarp();
-        }
-        if (!ok && lane == 0) atomicOr(&e.status[c], BNR_ST_PSI_NOTPD_);
-        // Y = A^-1 Lp'  (forward substitution; lane = column), then M = Y' Y (lanes over the R^2 entries)
-        if (lane < R) {
-          const int col = lane;
-          for (int i = 0; i < R; ++i) {
-            double sv = (col >= i) ? Lp[col + R * i] : 0.0;   // Lp'(i, col) = Lp(col, i)
-            for (int p = 0; p < i; ++p) sv -= Ab[i + R * p] * Yw[p + R * col];
-            Yw[i + R * col] = sv / Ab[i + R * i];
-          }
-        }
-        __syncwarp();
-        for (int en = lane; en < RR; en += 32) {
-          const int a = en % R, b = en / R;
-          double sv = 0.0;
-          for (int p = 0; p < R; ++p) sv += Yw[p + R * a] * Yw[p + R * b];
-          e.M[(size_t)c * RR + a + R * b] = sv;
-        }
-        if (e.aux.m_params) {
-          double* o = e.aux.m_params + (size_t)c * (1 + 2 * RR);
-          if (lane == 0) o[0] = df;
-          for (int en = lane; en < RR; en += 32) {
-            const int a = en % R, b = en / R;
-            o[1 + a + R * b] = psi[a + R * b];
-            o[1 + RR + a + R * b] = (a >= b) ? Lp[a + R * b] : 0.0;
-          }
-        }
-      }
-    }
   }
-
-  if (mask & (1 << BNR_COND_MU_)) {
-    double s = 0.0;
-    for (int i = tid; i < d.n; i += blockDim.x) s += e.y[i] - e.xg[(size_t)c * d.np + i];
-    s = block_sum(s, red);
-    if (tid == 0) {
-      const double m = s / d.n, sd = sqrt(e.tau2[c] / d.n);
-      DrawStream st(key, (uint32_t)it, SITE_MU, 0, injc ? injc + L.mu : nullptr, 1);
-      e.mu[c] = m + sd * st.normal();
-      if (e.aux.mu_params) { e.aux.mu_params[2 * c] = m; e.aux.mu_params[2 * c + 1] = sd; }
-    }
+  if (do_mu) {
+    for (int i = tid; i < d.n; i += blockDim.x) sy += e.y[i] - e.xg[(size_t)c * d.np + i];
+    sy = block_sum(sy, red);
   }
+  __syncthreads();                 // us, sums complete
+  double* Lp = psi + RR;           // chol(Psi), lower
+  double* Ab = Lp + RR;            // Bartlett factor, lower
+  double* Yw = Ab + RR;            // Y = A^-1 Lp'
+  const double df = d.nu + nz;
 
-  __syncthreads();
-  if ((mask & ((1 << BNR_COND_LAMBDA_) | (1 << BNR_COND_PI_))) && tid < R) {
-    const int r = tid;
+  if (warp == 0 && do_M) {
+    // Psi = I + sum_k u_k u_k'
+    for (int en = lane; en < RR; en += 32) {
+      const int a = en % R, b = en / R;
+      double s = (a == b) ? 1.0 : 0.0;
+      for (int k = 0; k < V; ++k) s += us[k * R + a] * us[k * R + b];
+      psi[en] = s;
+      Lp[en] = s;
+    }
+  } else if (warp == 1 && lane == 0 && do_theta) {
+    const double shape = d.zeta + 0.5 * (double)V * (V + 1);
+    const double scale = 2.0 / (2.0 * d.iota + sums[2 * R]);
+    DrawStream st(key, (uint32_t)it, SITE_THETA, 0, injc ? injc + L.theta : nullptr, 1);
+    e.theta[c] = st.gamma(shape) * scale;
+    if (e.aux.theta_params) { e.aux.theta_params[2 * c] = shape; e.aux.theta_params[2 * c + 1] = scale; }
+  } else if (warp == 2 && lane == 0 && do_delta) {
+    const double a = d.a_delta + sx, b = d.b_delta + ((double)V - sx);
+    DrawStream st(key, (uint32_t)it, SITE_DELTA, 0, injc ? injc + L.Delta : nullptr, 3);
+    double dl;
+    if (a > 0.0 && b > 0.0) {
+      const double ga = st.gamma(a), gb = st.gamma(b);
+      dl = ga / (ga + gb);
+    } else if (a > 0.0) dl = 1.0;
+    else if (b > 0.0) dl = 0.0;
+    else {
+      if (injc) { st.pos = 2; }
+      dl = (st.uniform() < 0.5) ? 0.0 : 1.0;
+    }
+    e.Delta[c] = dl;
+    if (e.aux.delta_params) { e.aux.delta_params[2 * c] = a; e.aux.delta_params[2 * c + 1] = b; }
+  } else if (warp == 3 && lane == 0 && do_mu) {
+    const double m = sy / d.n, sd = sqrt(e.tau2[c] / d.n);
+    DrawStream st(key, (uint32_t)it, SITE_MU, 0, injc ? injc + L.mu : nullptr, 1);
+    e.mu[c] = m + sd * st.normal();
+    if (e.aux.mu_params) { e.aux.mu_params[2 * c] = m; e.aux.mu_params[2 * c + 1] = sd; }
+  } else if (warp >= 4 && warp <= 6 && do_M) {
+    // Bartlett variates, one Philox stream per variate (element = its index): R chi-squares (diagonal), then the
+    // strictly-lower normals row by row -- the same order as the injected layout
+    const int nvar = R + R * (R - 1) / 2;
+    for (int v = (warp - 4) * 32 + lane; v < nvar; v += 96) {
+      DrawStream st(key, (uint32_t)it, SITE_M, (uint32_t)v, injc ? injc + L.M + v : nullptr, 1);
+      if (v < R) {
+        const double ci = injc ? st.uniform() : 2.0 * st.gamma(0.5 * (df - v));
+        Ab[v + R * v] = sqrt(ci);
+      } else {
+        int i = 1, rem = v - R;
+        while (rem >= i) { rem -= i; ++i; }
+        Ab[i + R * rem] = st.normal();
+      }
+    }
+  } else if (warp == 7 && lane < R && (do_lam || do_pi)) {
+    const int r = lane;
     const double vals[3] = {0.0, 1.0, -1.0};
     double lam_new = e.lambda[c * R + r];
-    if (mask & (1 << BNR_COND_LAMBDA_)) {
+    if (do_lam) {
       // loglik_v - loglik_(current) = (v - lam) A_r - 1/2 (v - lam)^2 B_r ; every r uses the OLD lambda elsewhere
       const double lam = lam_new, Ar = sums[r], Br = sums[R + r];
       double dl[3], mx = -1e300;
@@ -581,7 +551,7 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
       lam_new = vals[i];
       if (tot != tot) atomicOr(&e.status[c], BNR_ST_NAN_);
     }
-    if (mask & (1 << BNR_COND_PI_)) {
+    if (do_pi) {
       double al[3] = {pow((double)(r + 1), d.eta), 1.0, 1.0};
       if (lam_new == 1.0) al[1] += 1.0;
       else if (lam_new == 0.0) al[0] += 1.0;
@@ -594,8 +564,53 @@ __global__ void __launch_bounds__(256) k_finish(Engine e, int mask) {
         if (e.aux.pi_alpha) e.aux.pi_alpha[(size_t)c * 3 * R + r + R * v] = al[v];
       }
     }
-    // lambda is written last: the pi weights above and every other r read the OLD lambda / pi
-    if (mask & (1 << BNR_COND_LAMBDA_)) e.lambda[c * R + r] = lam_new;
+    // (every r reads and writes only its own lambda_r / pi_r)
+    if (do_lam) e.lambda[c * R + r] = lam_new;
+  }
+  if (!do_M) return;
+  __syncthreads();                 // Psi / Lp (warp 0) and the Bartlett factor (warps 4-6) are in shared memory
+  if (warp == 0) {
+    // Cholesky of Psi, column by column: lane i owns row i (same summation order as small_chol)
+    bool ok = true;
+    for (int j = 0; j < R; ++j) {
+      double sdot = 0.0;
+      if (lane >= j && lane < R) {
+        sdot = Lp[lane + R * j];
+        for (int p = 0; p < j; ++p) sdot -= Lp[lane + R * p] * Lp[j + R * p];
+      }
+      const double dj = __shfl_sync(0xffffffffu, sdot, j);
+      if (!(dj > 0.0)) ok = false;
+      const double rt = sqrt(dj);
+      if (lane == j) Lp[j + R * j] = rt;
+      else if (lane > j && lane < R) Lp[lane + R * j] = sdot / rt;
+      __syncwarp();
+    }
+    if (!ok && lane == 0) atomicOr(&e.status[c], BNR_ST_PSI_NOTPD_);
+    // Y = A^-1 Lp'  (forward substitution; lane = column), then M = Y' Y (lanes over the R^2 entries)
+    if (lane < R) {
+      const int col = lane;
+      for (int i = 0; i < R; ++i) {
+        double sv = (col >= i) ? Lp[col + R * i] : 0.0;   // Lp'(i, col) = Lp(col, i)
+        for (int p = 0; p < i; ++p) sv -= Ab[i + R * p] * Yw[p + R * col];
+        Yw[i + R * col] = sv / Ab[i + R * i];
+      }
+    }
+    __syncwarp();
+    for (int en = lane; en < RR; en += 32) {
+      const int a = en % R, b = en / R;
+      double sv = 0.0;
+      for (int p = 0; p < R; ++p) sv += Yw[p + R * a] * Yw[p + R * b];
+      e.M[(size_t)c * RR + a + R * b] = sv;
+    }
+    if (e.aux.m_params) {
+      double* o = e.aux.m_params + (size_t)c * (1 + 2 * RR);
+      if (lane == 0) o[0] = df;
+      for (int en = lane; en < RR; en += 32) {
+        const int a = en % R, b = en / R;
+        o[1 + a + R * b] = psi[a + R * b];
+        o[1 + RR + a + R * b] = (a >= b) ? Lp[a + R * b] : 0.0;
+      }
+    }
   }
 }
 
@@ -819,8 +834,13 @@ void small_kernels_setup() {
   cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 
+int tau2_blocks(int q) {
+  int nb = (q + 1023) / 1024;
+  return nb < 1 ? 1 : (nb > TAU2_MAX_BLOCKS ? TAU2_MAX_BLOCKS : nb);
+}
 void launch_tau2(const Engine& e, cudaStream_t s) {
-  ++g_launches; k_tau2<<<e.d.C, 256, smem_u(e.d), s>>>(e);
+  dim3 grid(tau2_blocks(e.d.q), e.d.C);
+  ++g_launches; k_tau2<<<grid, 256, smem_u(e.d), s>>>(e);
 }
 void launch_uxi(const Engine& e, cudaStream_t s) {
   const Dims& d = e.d;

@@ -69,6 +69,12 @@ class Engine:
         self.close()
 
     @property
+    def chain_groups(self):
+        v = C.c_int32()
+        check(self._L.bnr_chain_groups(self._h, C.byref(v)))
+        return int(v.value)
+
+    @property
     def gamma_mode(self):
         """"nform" (the reference's n x n Bhattacharya draw) or "qform" (q x q precision Cholesky)."""
         v = C.c_int32()
@@ -177,11 +183,31 @@ class Engine:
     def export_ess(self, acov_dev_ptr, means_dev_ptr):
         check(self._L.bnr_export_ess(self._h, C.c_void_p(acov_dev_ptr), C.c_void_p(means_dev_ptr)))
 
-    def ess_from_stats(self, acov_ptr, nparts, means_ptr, total_chains, nrows, max_lag):
+    def ess_from_stats(self, acov_ptr, nparts, means_ptr, total_chains, nrows, max_lag, with_lags=False):
+        """(ESS xi, ESS gamma) from gathered statistics; with_lags also returns the lags each Geyer sequence consumed
+        (max_lag + 1 = not terminated inside the lag budget)."""
         ex, eg = np.empty(self.V), np.empty(self.q)
-        check(self._L.bnr_ess_from_stats(self.device, C.c_void_p(acov_ptr), int(nparts), C.c_void_p(means_ptr),
-                                         int(total_chains), self.V, self.q, int(nrows), int(max_lag), _dp(ex), _dp(eg)))
-        return ex, eg
+        lx, lg = np.empty(self.V), np.empty(self.q)
+        check(self._L.bnr_ess_from_stats_lags(self.device, C.c_void_p(acov_ptr), int(nparts), C.c_void_p(means_ptr),
+                                              int(total_chains), self.V, self.q, int(nrows), int(max_lag),
+                                              _dp(ex), _dp(eg), _dp(lx), _dp(lg)))
+        return (ex, eg, lx, lg) if with_lags else (ex, eg)
+
+    def ess_stream_begin(self, max_lag, ndraws):
+        """Accumulate the ESS statistics of the next `ndraws` sweeps on the device while they run (no traces)."""
+        check(self._L.bnr_ess_stream_begin(self._h, int(max_lag), int(ndraws)))
+        self._last_ess_rows = int(ndraws)
+
+    def ess_stream_finish(self):
+        check(self._L.bnr_ess_stream_finish(self._h))
+
+    def ess_streamed(self):
+        """(ESS xi, ESS gamma) of this handle's chains from the streamed statistics (after ess_stream_finish)."""
+        (pa, _), (pm, _), lag = self.ess_device()
+        return self.ess_from_stats(pa, 1, pm, self.C, self._ess_rows(), lag)
+
+    def _ess_rows(self):
+        return self._last_ess_rows
 
     def export_moments(self, dev_ptr):
         check(self._L.bnr_export_moments(self._h, C.c_void_p(dev_ptr)))

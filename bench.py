@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Benchmark of the Gibbs hot path (BASELINE.json metric: Gibbs iterations/s summed over all chains).
+"""Benchmark of the Gibbs hot path (BASELINE.json metric: Gibbs iterations/s summed over all chains; gamma ESS/s).
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine (libbnr.so through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU cores
@@ -10,13 +10,30 @@ HEAD convention), n=1000 samples, R=7, 64 chains per GPU (weak scaling: N GPUs a
 global chain ids key the RNG; the only exchange is an NCCL all-gather of split-half moments for R-hat).
 Inputs are larger than L2 by construction (the per-sweep working set is 64 x 8 MB Gram matrices = 512 MB >> 126 MB),
 so no explicit L2 flush is needed between timed iterations.
+
+Legs of the default run (every number in the JSON line is measured in this run unless its key says otherwise):
+  value          K timed sweeps, inputs resident in HBM, CUDA events on the handle's stream, max over ranks
+  roofline       the dominant kernel (Gram SYRK) timed alone with CUDA events; FP64 peak = cuBLAS DGEMM in this run
+  e2e            Fit(X, y, R; ...) + Summary through the public API with HOST buffers (H2D / D2H inside the timed region)
+  strong_scaling BASELINE config 3 as written: 64 chains IN TOTAL split over the N GPUs (= value at N = 1)
+  gamma_ess_per_sec  a separate leg: burn-in sweeps, then retained draws of every chain, device-side multi-chain Geyer
+                 ESS of every gamma_j, divided by the device time of burn-in + draws
+  other_configs  BASELINE configs 2, 4, 5 on one GPU (N = 1 only): ms/sweep, chain-iterations/s, roofline fraction
+  cpu_baseline   the reference's algorithm (NumPy/OpenBLAS port, Julia is absent) on the host cores (N = 1 only)
 """
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the CPU arm runs one single-threaded chain per process (src/gibbs.jl:946-948): pin every BLAS / OpenMP pool
+    # BEFORE NumPy is imported (the timing itself additionally runs in a child interpreter, oracle/cpu_baseline.py)
+    for _v in ("OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "OMP_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = "1"
+
 import argparse
 import json
 import math
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -59,39 +76,88 @@ def synth(cfg_name, dense=False):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU, sampled through NVML every `period` seconds (falls back to the
+    B200_PROFILING.md nvidia-smi query when NVML cannot be loaded).  `mark()` / `unmark()` bracket the timed region so
+    that the record says how many samples fell INSIDE it."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None, period=0.01):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.uuid, self.period = index, uuid, period
+        self.rows, self._stop_evt, self._in = [], threading.Event(), False
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand if isinstance(cand, bytes) else cand.encode())
+                        break
+                    except Exception:
+                        try:
+                            h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                            break
+                        except Exception:
+                            h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def mark(self):
+        self._in = True
+
+    def unmark(self):
+        self._in = False
+
+    def _reasons(self):
+        nv = self.nv
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            if hasattr(nv, fn):
+                try:
+                    return int(getattr(nv, fn)(self.h))
+                except Exception:
+                    continue
+        return 0
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([t.strip() for t in out.strip().split(",")])
+                if self.nv is not None:
+                    sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    mask = self._reasons()
+                    self.rows.append((sm, self.max_mhz, [n for n, b in self.BITS if mask & b], self._in))
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    r = [t.strip() for t in out.strip().split(",")]
+                    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                    self.rows.append((float(r[0]), float(r[1]),
+                                      [n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")], self._in))
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(self.period if self.nv is not None else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=3)
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
-                    samples=len(sm))
+        inside = [r for r in self.rows if r[3]]
+        use = inside if len(inside) >= 5 else self.rows
+        sm = [r[0] for r in use]
+        reasons = sorted({n for r in use for n in r[2]})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_min_mhz=float(np.min(sm)) if sm else None,
+                    sm_max_mhz=max([r[1] for r in self.rows], default=None), reasons=reasons,
+                    samples=len(use), samples_in_timed_region=len(inside),
+                    window="timed region" if use is inside else "warm-up + timed region (timed region too short for 5 samples)",
+                    source="nvml" if self.nv is not None else "nvidia-smi")
 
 
 def fp64_peak_tflops(torch, dev):
@@ -113,29 +179,42 @@ def fp64_peak_tflops(torch, dev):
     return best
 
 
+def cpu_port_sample(X, y, R, chains, sweeps, warm):
+    """The reference's algorithm on the host cores: one single-threaded chain per process, min(chains, cores) of them
+    at once (oracle/cpu_baseline.py).  Returns the cpu_baseline object and the raw timing record."""
+    from oracle import cpu_baseline as B
+    r = B.time_port(np.ascontiguousarray(X), y, R, chains, sweeps, warm=warm)
+    cpu = {"value": r["value"], "unit": "chain-iterations/s", "cores": r["nproc"], "kind": "port",
+           "threads_per_proc": r["threads_per_proc"], "chains": r["nproc"], "sweeps": r["sweeps"],
+           "per_core": r["value"] / r["nproc"], "timed_s": r["timed_s"],
+           "sample": "%d chains x %d sweeps (+%d warm-up) of the same workload, one single-threaded chain per process "
+                     "(BLAS pools pinned to 1 thread before NumPy loads, asserted in every worker), barrier-timed %.1f s; "
+                     "NumPy/OpenBLAS port of gibbs_sample!'s dense formulation (Julia is absent)"
+                     % (r["nproc"], r["sweeps"], r["warm"], r["timed_s"])}
+    return cpu, r
+
+
 def run_reference(args, rank):
-    """The reference's algorithm on the host cores (oracle/cpu_baseline.py: dense formulation, one chain per process)."""
+    """`--impl reference`: the reference's own CPU path (port) on all host cores, same config / metric / unit.
+    One step = one sweep of the min(64, cores) chains that run concurrently (the bounded sample of the 64-chain
+    workload); exactly `steps` timed sweeps after `warmup` untimed ones are run and reported."""
     if rank != 0:
         return
-    from oracle import cpu_baseline as B
     X, y, dims = synth(args.config, args.dense)
     chains = CONFIGS[args.config]["chains"]
-    sweeps = max(1, min(args.steps, args.ref_sweeps))
-    t_all = []
-    for _ in range(1):
-        its, nproc, wall = B.time_port(np.ascontiguousarray(X), y, dims["R"], chains, sweeps, warm=max(1, min(args.warmup, 1)))
-        t_all.append(its)
-    val = float(np.mean(t_all))
+    sweeps = max(1, min(args.steps, args.ref_max_sweeps))
+    warm = max(1, min(args.warmup, 3))
+    cpu, r = cpu_port_sample(X, y, dims["R"], chains, sweeps, warm)
+    val = cpu["value"]
     line = {
         "impl": "reference", "metric": "gibbs_iters_per_sec_all_chains", "value": val, "unit": "chain-iterations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nproc / val,
+        "n_gpus": args.gpus, "steps": sweeps, "warmup": warm, "ms_per_step": 1e3 * r["timed_s"] / sweeps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, dims, chains),
-        "cpu_baseline": {"value": val, "unit": "chain-iterations/s", "cores": nproc, "kind": "port",
-                         "sample": "%d chains x %d sweeps (+1 warm-up) of the same workload, one chain per process, "
-                                   "BLAS threads = 1; Julia absent, NumPy/OpenBLAS port of gibbs_sample!" % (nproc, sweeps)},
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "chain-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "wall_s": r["wall_s"],
     }
     print(json.dumps(line), flush=True)
 
@@ -160,6 +239,27 @@ def workload_config(args, dims, chains):
             "parallelism": "chains sharded over GPUs, %d per GPU" % chains}
 
 
+def algo_flops(n, q):
+    """min of the n-form (n^2 q + n^3/3 + 2 n^2 + 10 n q) and the q-form (q^3/3 + 4 q^2 + 6 n q)."""
+    return min(n * n * q + n ** 3 / 3.0 + 2.0 * n * n + 10.0 * n * q, q ** 3 / 3.0 + 4.0 * q * q + 6.0 * n * q)
+
+
+def dominant_kernel(eng, phases, n, q, chains):
+    """(name, ms per launch, algorithmic flops per launch) of the kernel that bounds the sweep."""
+    if eng.gamma_mode == "nform":
+        # G = X D X' + I.  SURVEY 8(d): n^2 q flops per chain-iteration (lower half, mul + add)
+        return ("k_gram_syrk (X diag(S) X' + I, DMMA m8n8k4, TMA ring)", phases["syrk"], chains * float(n) * n * q)
+    # q-form: the batched blocked Cholesky of the q x q precision dominates; q^3/3 flops per chain-iteration
+    return ("blocked Cholesky of P = (X'X + D^-1)/tau2 (k_chol_panel + k_chol_update)", phases["cholesky"],
+            chains * float(q) ** 3 / 3.0)
+
+
+def time_sweeps(eng, K):
+    """K sweeps timed with CUDA events on the handle's stream (bnr_last_run_ms)."""
+    eng.run(K, sync=True)
+    return eng.last_run_ms()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,14 +269,21 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the config's)")
     ap.add_argument("--total-chains", type=int, default=0,
-                    help="strong scaling: this many chains in total, split evenly over the GPUs (BASELINE config 3 "
-                         "quotes 64 chains across 1/2/4/8 GPUs); default is weak scaling with the config's chains per GPU")
+                    help="strong scaling as the headline: this many chains in total, split evenly over the GPUs; default "
+                         "is weak scaling with the config's chains per GPU (the strong-scaling figure of BASELINE config 3, "
+                         "64 chains in total, is always reported beside it in `strong_scaling`)")
     ap.add_argument("--chain-groups", type=int, default=0, help="independent stream/graph groups per GPU (0 = library default)")
     ap.add_argument("--gamma-mode", default="auto", choices=["auto", "nform", "qform"])
     ap.add_argument("--dense", action="store_true", help="dense Gaussian X instead of sparse networks")
-    ap.add_argument("--ref-sweeps", type=int, default=12, help="bounded CPU sample: sweeps per chain")
+    ap.add_argument("--ref-max-sweeps", type=int, default=200, help="reference arm: cap on the timed sweeps")
+    ap.add_argument("--cpu-sweeps", type=int, default=10, help="cpu_baseline leg of our arm: timed sweeps per chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-sweeps", type=int, default=5)
+    ap.add_argument("--ess-burn", type=int, default=1000, help="ESS leg: burn-in sweeps (0 with --ess-draws 0 skips the leg)")
+    ap.add_argument("--ess-draws", type=int, default=1000, help="ESS leg: retained draws per chain")
+    ap.add_argument("--ess-max-lag", type=int, default=255)
+    ap.add_argument("--no-other-configs", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +303,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     X, y, dims = synth(args.config, args.dense)
     chains = args.chains or CONFIGS[args.config]["chains"]
@@ -222,22 +329,41 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_stats(eng, nrows, lag):
+        """ESS of (xi, gamma) over the chains of all ranks from this rank's accumulated statistics."""
+        (pa, na), (pm, nm), lag = eng.ess_device()
+        if world == 1:
+            return eng.ess_from_stats(pa, 1, pm, eng.C, nrows, lag, with_lags=True)
+        a_mine = torch.empty(na, dtype=torch.float64, device=dev)
+        m_mine = torch.empty(nm, dtype=torch.float64, device=dev)
+        eng.export_ess(a_mine.data_ptr(), m_mine.data_ptr())
+        a_all = torch.empty(na * world, dtype=torch.float64, device=dev)
+        m_all = torch.empty(nm * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(a_all, a_mine)
+        dist.all_gather_into_tensor(m_all, m_mine)
+        torch.cuda.synchronize(dev)
+        return eng.ess_from_stats(a_all.data_ptr(), world, m_all.data_ptr(), eng.C * world, nrows, lag, with_lags=True)
+
     # ---------------- device-resident timing: `value` ----------------
-    rows = Wm + K + 1 + args.profile_sweeps + 2
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
+    sampler.start()
     eng = bnr.Engine(X, y, R, num_chains=chains, seed=20241018, chain_offset=rank * chains, device=local_rank,
-                     trace_rows=rows, trace_full_chains=1, trace_gamma_xi_all=True, chain_groups=args.chain_groups,
-                     gamma_mode=args.gamma_mode)
+                     trace_rows=0, chain_groups=args.chain_groups, gamma_mode=args.gamma_mode)
     eng.init_state()
     eng.run(Wm)
     eng.set_moment_window(Wm + 1, K)
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark()
     t0 = time.perf_counter()
     eng.run(K, sync=True)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler.unmark()
     dev_ms = eng.last_run_ms()
     clocks = sampler.stop()
     launches = eng.launch_count() - launches0
@@ -260,32 +386,6 @@ def main():
         rx, rg = eng.rhat()
     status = eng.status()
 
-    # gamma ESS/s of EVERY edge coefficient, on the device (bnr_ess_*: per-chain-centred autocovariances by direct
-    # lag sums + Geyer's initial monotone sequence); across GPUs the per-rank autocovariance sums and chain means are
-    # all-gathered over NCCL and reduced identically on every rank
-    max_lag = min(255, K - 1)
-    ess_x = ess_g = None
-    lag = 0
-    if K >= 4:
-        eng.ess_accumulate(Wm + 1, K, max_lag)
-        (pa, na), (pm, nm), lag = eng.ess_device()
-    if K < 4:
-        ess_g = np.full(q, np.nan)
-    elif world > 1:
-        a_mine = torch.empty(na, dtype=torch.float64, device=dev)
-        m_mine = torch.empty(nm, dtype=torch.float64, device=dev)
-        eng.export_ess(a_mine.data_ptr(), m_mine.data_ptr())
-        a_all = torch.empty(na * world, dtype=torch.float64, device=dev)
-        m_all = torch.empty(nm * world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(a_all, a_mine)
-        dist.all_gather_into_tensor(m_all, m_mine)
-        torch.cuda.synchronize(dev)
-        ess_x, ess_g = eng.ess_from_stats(a_all.data_ptr(), world, m_all.data_ptr(), chains * world, K, lag)
-    else:
-        ess_x, ess_g = eng.ess_from_stats(pa, 1, pm, chains, K, lag)
-    ess_med = float(np.nanmedian(ess_g)) if np.isfinite(ess_g).any() else float("nan")
-    ess_min = float(np.nanmin(ess_g)) if np.isfinite(ess_g).any() else float("nan")
-
     # ---------------- per-phase CUDA-event profile of eager sweeps (roofline numerator) ----------------
     phases = {}
     for _ in range(max(1, args.profile_sweeps)):
@@ -293,16 +393,8 @@ def main():
             phases.setdefault(k, []).append(v)
     phases = {k: float(np.mean(v)) for k, v in phases.items()}
     gmode = eng.gamma_mode
-    if gmode == "nform":
-        # dominant kernel: G = X D X' + I.  SURVEY 8(d): n^2 q flops per chain-iteration (lower half, mul+add)
-        dom_kernel = "k_gram_syrk (X diag(S) X' + I, DMMA m8n8k4, TMA ring)"
-        dom_ms = phases["syrk"]
-        dom_flops = chains * float(n) * n * q
-    else:
-        # q-form: the batched blocked Cholesky of the q x q precision dominates; q^3/3 flops per chain-iteration
-        dom_kernel = "blocked Cholesky of P = (X'X + D^-1)/tau2 (k_chol_update + k_potf2_inv + k_trsm_dmma)"
-        dom_ms = phases["cholesky"]
-        dom_flops = chains * float(q) ** 3 / 3.0
+    chain_groups = eng.chain_groups
+    dom_kernel, dom_ms, dom_flops = dominant_kernel(eng, phases, n, q, chains)
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "syrk_traffic.json")
@@ -332,17 +424,92 @@ def main():
     d2h = (res.state["gamma"].nbytes + res.state["xi"].nbytes + 8 * (V + q) + 8 * (3 * q + V)) / K
     assert (summ is None or len(summ.edge_coef["estimate"]) == q) and res.extra["tot_generated"] == K + 1
 
+    # ---------------- strong scaling: BASELINE config 3 as written, 64 chains IN TOTAL over the N GPUs ----------------
+    strong = None
+    total64 = CONFIGS[args.config]["chains"]
+    if not args.no_strong and not args.total_chains and total64 % world == 0:
+        cs = total64 // world
+        if world == 1 and cs == chains:
+            strong = {"total_chains": total64, "chains_per_gpu": cs, "value": value, "ms_per_step": step_ms,
+                      "chain_groups": chain_groups, "note": "identical to the headline run at N = 1"}
+        else:
+            e2 = bnr.Engine(X, y, R, num_chains=cs, seed=20241018, chain_offset=rank * cs, device=local_rank,
+                            trace_rows=0, chain_groups=args.chain_groups, gamma_mode=args.gamma_mode)
+            e2.init_state()
+            e2.run(Wm)
+            barrier()
+            ms2 = max_over_ranks(time_sweeps(e2, K))
+            strong = {"total_chains": total64, "chains_per_gpu": cs, "value": total64 * K / (ms2 * 1e-3),
+                      "ms_per_step": ms2 / K, "chain_groups": e2.chain_groups}
+            e2.close()
+
+    # ---------------- gamma ESS/s: burn-in, then retained draws of every chain, Geyer ESS on the device ----------------
+    ess = None
+    if args.ess_draws >= 8:
+        Bn, Dn = max(0, args.ess_burn), args.ess_draws
+        e3 = bnr.Engine(X, y, R, num_chains=chains, seed=20241019, chain_offset=rank * chains, device=local_rank,
+                        trace_rows=0, chain_groups=args.chain_groups, gamma_mode=args.gamma_mode)
+        e3.init_state()
+        barrier()
+        ms_burn = time_sweeps(e3, Bn) if Bn else 0.0
+        e3.ess_stream_begin(args.ess_max_lag, Dn)
+        ms_draw = time_sweeps(e3, Dn)
+        e3.ess_stream_finish()
+        ess_ms = max_over_ranks(ms_burn + ms_draw)
+        ex, eg, lag_x, lag_g = gather_stats(e3, Dn, args.ess_max_lag)
+        lag = e3.ess_device()[2]
+        e3.close()
+        fin = np.isfinite(eg)
+        ess = {"median": float(np.nanmedian(eg)) / (ess_ms * 1e-3) if fin.any() else None,
+               "min": float(np.nanmin(eg)) / (ess_ms * 1e-3) if fin.any() else None,
+               "mean": float(np.nanmean(eg)) / (ess_ms * 1e-3) if fin.any() else None,
+               "unit": "effective gamma draws per second (per edge coefficient; pooled over all chains)",
+               "ess_median": float(np.nanmedian(eg)) if fin.any() else None,
+               "ess_min": float(np.nanmin(eg)) if fin.any() else None,
+               "edges": int(q), "burn_in": Bn, "draws_per_chain": Dn, "chains": chains * world, "max_lag": int(lag),
+               "geyer_terminated_frac": float(np.mean(lag_g <= lag - 1)),
+               "seconds": ess_ms * 1e-3, "iters_per_sec_in_leg": world * chains * (Bn + Dn) / (ess_ms * 1e-3),
+               "estimator": "multi-chain Geyer initial monotone sequence on per-chain-centred autocovariances "
+                            "(streamed lagged products, no all-chain trace), seconds = device time of burn-in + draws"}
+
+    # ---------------- the other BASELINE configs on one GPU ----------------
+    others = None
+    if rank == 0 and world == 1 and not args.no_other_configs and args.config == "c3":
+        others = {}
+        for name in ("c2", "c4", "c5"):
+            Xo, yo, do = synth(name)
+            co = CONFIGS[name]["chains"]
+            eo = bnr.Engine(Xo, yo, do["R"], num_chains=co, seed=20241018, device=local_rank, trace_rows=0)
+            eo.init_state()
+            eo.run(10)
+            l0 = eo.launch_count()
+            Ko = 200
+            ms = time_sweeps(eo, Ko)
+            lo = eo.launch_count() - l0
+            ph = {}
+            for _ in range(3):
+                for k, v in eo.profile_sweep().items():
+                    ph.setdefault(k, []).append(v)
+            ph = {k: float(np.mean(v)) for k, v in ph.items()}
+            dk, dms, dfl = dominant_kernel(eo, ph, do["n"], do["q"], co)
+            its = co * Ko / (ms * 1e-3)
+            others[name] = {"V": do["V"], "q": do["q"], "n": do["n"], "R": do["R"], "chains": co,
+                            "ms_per_sweep": ms / Ko, "value": its, "unit": "chain-iterations/s",
+                            "gamma_mode": eo.gamma_mode, "chain_groups": eo.chain_groups,
+                            "launches_per_sweep": lo / Ko,
+                            "algorithmic_tflops": its * algo_flops(do["n"], do["q"]) / 1e12,
+                            "frac_of_fp64_peak_whole_sweep": its * algo_flops(do["n"], do["q"]) / 1e12 / peak,
+                            "dominant_kernel": dk, "dominant_ms": dms,
+                            "dominant_frac_of_peak": dfl / (dms * 1e-3) / 1e12 / peak,
+                            "phases_ms": ph, "status_or": int(np.bitwise_or.reduce(eo.status()))}
+            eo.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline as B
-        sweeps = max(2, min(args.ref_sweeps, 8))
-        its, nproc, wall = B.time_port(np.ascontiguousarray(X), y, R, chains, sweeps, warm=1)
-        cpu = {"value": its, "unit": "chain-iterations/s", "cores": nproc, "kind": "port",
-               "sample": "%d chains x %d sweeps (+1 warm-up), one chain per process, BLAS threads = 1, %.1f s wall; "
-                         "NumPy/OpenBLAS port of the reference's dense formulation (Julia absent)" % (nproc, sweeps, wall)}
+        cpu, _ = cpu_port_sample(X, y, R, chains, max(2, args.cpu_sweeps), 2)
 
     if rank == 0:
-        algo_flops = n * n * q + n ** 3 / 3.0 + 2.0 * n * n + 10.0 * n * q   # n-form, SURVEY 8(d)
+        af = algo_flops(n, q)
         line = {
             "metric": "gibbs_iters_per_sec_all_chains", "value": value, "unit": "chain-iterations/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms, "higher_is_better": True,
@@ -356,19 +523,23 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom_kernel,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": traffic, "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
+                         "traffic": traffic,
+                         "traffic_source": "offline: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu "
+                                           "--set full capture committed under profiles/ (not measured in this run)",
+                         "ms_per_launch": dom_ms, "flops_per_launch": dom_flops,
                          "peak_source": "cuBLAS DGEMM measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "peak_theoretical": 128 * 148 * 1.965e9 / 1e12,
                          "frac_of_theoretical": achieved / (128 * 148 * 1.965e9 / 1e12),
-                         "note": "theoretical = 128 FP64 flop/clk/SM (DMMA and DFMA alike) x 148 SMs x 1.965 GHz"},
+                         "whole_sweep_frac": value / world * af / 1e12 / peak,
+                         "note": "theoretical = 128 FP64 flop/clk/SM (DMMA and DFMA alike) x 148 SMs x 1.965 GHz; "
+                                 "whole_sweep_frac = algorithmic flops of the whole sweep / step time / peak"},
             "cpu_baseline": cpu,
-            "gamma_ess_per_sec": {"median": ess_med / (total_ms * 1e-3),
-                                  "min": ess_min / (total_ms * 1e-3),
-                                  "edges": int(q), "draws_per_chain": K, "chains": chains * world, "max_lag": lag,
-                                  "note": "device-side multi-chain Geyer ESS of every gamma_j over the timed draws "
-                                          "(short window right after warm-up: indicative, not a converged-run figure)"},
+            "gamma_ess_per_sec": ess,
+            "strong_scaling": strong,
+            "other_configs": others,
             "gamma_mode": gmode,
-            "algorithmic_tflops": value * algo_flops / 1e12,
+            "chain_groups": chain_groups,
+            "algorithmic_tflops": value * af / 1e12,
             "phases_ms": phases,
             "wall_ms_per_step": wall_ms / K,
             "rhat": {"max_gamma": float(np.nanmax(rg)) if np.isfinite(rg).any() else None, "max_xi": float(np.nanmax(rx[np.isfinite(rx)])) if np.isfinite(rx).any() else None,

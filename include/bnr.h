@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BNR_VERSION 102
+#define BNR_VERSION 200
 
 /* error codes */
 #define BNR_OK 0
@@ -224,6 +224,21 @@ int bnr_ess_from_stats(int device, const double* dev_acov_parts, int32_t nparts,
                        int32_t total_chains, int32_t V, int32_t q, int64_t nrows, int32_t max_lag, double* ess_xi,
                        double* ess_gamma);
 
+/* as bnr_ess_from_stats, plus the number of lags each Geyer sequence consumed (max_lag + 1 = the sequence had not
+ * terminated inside the lag budget: that ESS is an upper bound); lags_* may be NULL */
+int bnr_ess_from_stats_lags(int device, const double* dev_acov_parts, int32_t nparts, const double* dev_chain_means,
+                            int32_t total_chains, int32_t V, int32_t q, int64_t nrows, int32_t max_lag,
+                            double* ess_xi, double* ess_gamma, double* lags_xi, double* lags_gamma);
+/* Streaming ESS statistics: the next `ndraws` sweeps accumulate their lagged products on the device while they run
+ * (ring of the last max_lag + 8 centred draws + [max_lag + 1] products per chain and parameter), so NO chain needs a
+ * trace (64 chains x 20 000 draws x 5150 parameters of traces would be 53 GB).  After those sweeps
+ * bnr_ess_stream_finish fills the same two statistics buffers as bnr_ess_accumulate: bnr_ess_device / bnr_export_ess /
+ * bnr_ess_from_stats then work unchanged (nrows = ndraws).  max_lag is clamped like in bnr_ess_accumulate. */
+int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndraws);
+int bnr_ess_stream_finish(bnr_handle* h);
+
+/* chain groups (independent streams / CUDA graphs) the handle runs */
+int bnr_chain_groups(bnr_handle* h, int32_t* groups);
 /* which gamma formulation the handle runs (BNR_GAMMA_NFORM / BNR_GAMMA_QFORM; AUTO is resolved at create) */
 int bnr_gamma_mode(bnr_handle* h, int32_t* mode);
 /* number of CUDA kernels launched by bnr_run on this handle so far (graph replays counted per kernel node) */

@@ -5,8 +5,9 @@ the reference's *formulation and BLAS/LAPACK calls* (src/gibbs.jl:267-636): the 
 `X tau2D X'` followed by an LU solve for gamma, a dense (V-1)-dimensional covariance Cholesky per node for the
 xi odds, three W rebuilds per latent dimension for lambda -- and replaces only what Julia would compile to
 tight scalar loops (GIG rejection loops, element-wise maps, sum_kbn) by vectorised NumPy, so that Python
-interpreter overhead is not charged to the reference.  One chain per process, OPENBLAS/MKL threads pinned to
-1, min(num_chains, cores) processes, exactly like one chain per Distributed.jl worker (src/gibbs.jl:946-948).
+interpreter overhead is not charged to the reference.  One chain per process, OPENBLAS/MKL/OpenMP threads pinned to
+1 *before NumPy is loaded* (the timing runs in a child interpreter, every worker asserts a 1-thread pool),
+min(num_chains, cores) processes, exactly like one chain per Distributed.jl worker (src/gibbs.jl:946-948).
 It is labelled kind="port" in bench.py.  Its draws are validated against the conditionals of bnr_oracle.py in
 tests/test_cpu_baseline.py.
 """
@@ -254,35 +255,112 @@ class ReferencePort:
         return new
 
 
+PIN_VARS = ("OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "OMP_NUM_THREADS", "NUMEXPR_NUM_THREADS",
+            "VECLIB_MAXIMUM_THREADS", "BLIS_NUM_THREADS")
+
+
+def blas_threads():
+    """Largest thread-pool size of any BLAS/OpenMP runtime loaded into this process (threadpoolctl)."""
+    from threadpoolctl import threadpool_info
+    return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+
+
 def _worker(args):
-    X, y, R, seed, warm, sweeps = args
+    """One chain = one process (src/gibbs.jl:946-948).  The pool is forked from an interpreter whose BLAS was loaded
+    with *_NUM_THREADS=1 (see time_port); this is asserted here, inside the worker, before anything is timed."""
+    X, y, R, seed, warm, sweeps, barrier = args
+    from threadpoolctl import threadpool_limits
+    threadpool_limits(1)                       # belt and braces: also caps a pool that was sized before the fork
+    nthr = blas_threads()
+    if nthr != 1:
+        raise RuntimeError("CPU baseline worker has a %d-thread BLAS pool; it must be 1" % nthr)
     port = ReferencePort(X, y, R, seed)
     for _ in range(warm):
         port.sweep()
+    barrier.wait()                             # every chain has warmed up: the timed region starts together
     t0 = time.perf_counter()
     for _ in range(sweeps):
         port.sweep()
-    return time.perf_counter() - t0
+    t1 = time.perf_counter()
+    barrier.wait()
+    return t0, t1, nthr
 
 
-def time_port(X, y, R, chains, sweeps, warm=1, nproc=None):
-    """Run `chains` independent chains, one per process, min(chains, cores) at a time (all concurrently when
-    chains <= cores).  Returns (iterations/s summed over chains, processes used, wall seconds)."""
-    import multiprocessing as mp
-    for var in ("OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "OMP_NUM_THREADS"):
-        os.environ[var] = "1"
+def host_cores():
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
-    nproc = min(chains, cores) if nproc is None else nproc
+    return cores
+
+
+def _time_port_here(X, y, R, nproc, sweeps, warm):
+    """Runs in an interpreter that was STARTED with the BLAS pools pinned to one thread."""
+    import multiprocessing as mp
     ctx = mp.get_context("fork")
+    mgr_barrier = ctx.Barrier(nproc)
+    procs, q = [], ctx.Queue()
+
+    def run(c):
+        try:
+            q.put((c, _worker((X, y, R, 1000 + c, warm, sweeps, mgr_barrier))))
+        except BaseException as exc:          # a dead worker must not leave the others at the barrier
+            mgr_barrier.abort()
+            q.put((c, exc))
+
+    for c in range(nproc):
+        p = ctx.Process(target=run, args=(c,))
+        p.start()
+        procs.append(p)
+    res = [q.get() for _ in range(nproc)]
+    for p in procs:
+        p.join()
+    for _, r in res:
+        if isinstance(r, BaseException):
+            raise r
+    t0 = min(r[0] for _, r in res)
+    t1 = max(r[1] for _, r in res)
+    return dict(timed_s=t1 - t0, threads_per_proc=max(r[2] for _, r in res), nproc=nproc, sweeps=sweeps, warm=warm)
+
+
+def time_port(X, y, R, chains, sweeps, warm=1, nproc=None):
+    """Time `sweeps` Gibbs sweeps of min(chains, cores) independent chains, one single-threaded chain per process,
+    all concurrently (one chain per Distributed.jl worker, src/gibbs.jl:946-948).
+
+    The BLAS thread pools are sized when NumPy is first imported, so setting *_NUM_THREADS afterwards (or in a forked
+    child) does nothing: the measurement therefore runs in a CHILD INTERPRETER started with the variables already in
+    its environment, every worker asserts a 1-thread pool, and the timed region is bracketed by barriers (start-up,
+    data transfer and warm-up are outside it).  Returns a dict: value (chain-iterations/s summed over the chains),
+    nproc, threads_per_proc, sweeps, warm, timed_s, wall_s."""
+    import json
+    import subprocess
+    import sys
+    import tempfile
+    nproc = min(chains, host_cores()) if nproc is None else nproc
+    env = dict(os.environ)
+    for var in PIN_VARS:
+        env[var] = "1"
     t0 = time.perf_counter()
-    with ctx.Pool(nproc) as pool:
-        pool.map(_worker, [(X, y, R, 1000 + c, warm, sweeps) for c in range(nproc)])
-    wall = time.perf_counter() - t0
-    # throughput of the timed sweeps only (process start-up and warm-up excluded is not possible across
-    # processes without a barrier; warm-up is one sweep, so it is charged: conservative for the CPU by < 1/sweeps)
-    its = nproc * (sweeps + warm) / wall
-    return its, nproc, wall
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "xy.npz")
+        np.savez(path, X=np.ascontiguousarray(X), y=np.asarray(y))
+        cmd = [sys.executable, os.path.abspath(__file__), path, str(int(R)), str(int(nproc)), str(int(sweeps)),
+               str(int(warm))]
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("CPU baseline child failed:\n" + out.stderr[-2000:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["wall_s"] = time.perf_counter() - t0
+    r["value"] = r["nproc"] * r["sweeps"] / r["timed_s"]
+    return r
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    _path, _R, _nproc, _sweeps, _warm = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    if blas_threads() != 1:
+        raise SystemExit("BLAS pool of the timing interpreter is not single-threaded: %d" % blas_threads())
+    _d = np.load(_path)
+    print(json.dumps(_time_port_here(_d["X"], _d["y"], _R, _nproc, _sweeps, _warm)))

@@ -27,7 +27,7 @@ def test_header_symbols_exported(bnr):
         assert hasattr(lib, name), "libbnr.so does not export " + name
     from bnr_b200 import capi
     assert sorted(capi.PROTOTYPES) == syms, "ctypes prototypes and include/bnr.h disagree"
-    assert bnr.lib().bnr_version() == 102
+    assert bnr.lib().bnr_version() == 200
 
 
 def test_params_struct_matches_header(bnr):

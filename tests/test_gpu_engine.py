@@ -400,6 +400,53 @@ def test_device_summary_and_ess_match_oracle(bnr, golden):
         np.testing.assert_array_equal(eg1, eg)
 
 
+@pytest.mark.parametrize("nsamp,L,groups", [(333, 63, 1), (100, 255, 2), (37, 15, 3), (64, 63, 2)])
+def test_streamed_ess_equals_trace_ess(bnr, golden, nsamp, L, groups):
+    """bnr_ess_stream_*: lagged products accumulated while the chains run (no traces) give the same statistics, hence
+    the same ESS, as the two-pass kernels over the recorded traces of the same draws -- for window lengths that are
+    and are not multiples of the 8-draw accumulation block, lag budgets above and below the window, odd chain groups."""
+    X, y = golden["test1.X"], golden["test1.y"]
+    nburn, C = 41, 5
+    with bnr.Engine(X, y, 5, num_chains=C, seed=11, trace_rows=nburn + nsamp + 1, trace_full_chains=0,
+                    chain_groups=groups) as eng:
+        eng.init_state()
+        eng.run(nburn)
+        eng.ess_stream_begin(L, nsamp)
+        eng.run(nsamp - 5)
+        eng.run(5)                                   # a window may span several bnr_run calls (odd counts run eagerly)
+        eng.ess_stream_finish()
+        (pa, na), (pm, nm), lag = eng.ess_device()
+        P = eng.V + eng.q
+        want_lag = min(L, nsamp - 1)
+        assert lag == (want_lag if want_lag % 2 else want_lag - 1)
+        import torch
+        acov_s = torch.empty(na, dtype=torch.float64, device="cuda")
+        mean_s = torch.empty(nm, dtype=torch.float64, device="cuda")
+        eng.export_ess(acov_s.data_ptr(), mean_s.data_ptr())
+        exs, egs = eng.ess_from_stats(pa, 1, pm, C, nsamp, lag)
+        # the same draws through the trace kernels
+        ext, egt = eng.ess(nburn + 1, nsamp, L)
+        acov_t = torch.empty(na, dtype=torch.float64, device="cuda")
+        mean_t = torch.empty(nm, dtype=torch.float64, device="cuda")
+        eng.export_ess(acov_t.data_ptr(), mean_t.data_ptr())
+        a_s, a_t = acov_s.cpu().numpy().reshape(lag + 1, P), acov_t.cpu().numpy().reshape(lag + 1, P)
+        scale = np.abs(a_t[0])[None, :] + 1e-300
+        assert np.max(np.abs(a_s - a_t) / scale) < 1e-11
+        np.testing.assert_allclose(mean_s.cpu().numpy(), mean_t.cpu().numpy(), rtol=1e-13, atol=1e-13)
+        ok = np.isfinite(egt)
+        np.testing.assert_allclose(egs[ok], egt[ok], rtol=1e-7)
+        assert (np.isnan(exs) == np.isnan(ext)).all()
+        okx = np.isfinite(ext)
+        np.testing.assert_allclose(exs[okx], ext[okx], rtol=1e-7)
+        # a second window on the same handle reuses the buffers
+        eng.ess_stream_begin(L, 16)
+        eng.run(16)
+        eng.ess_stream_finish()
+        assert np.isfinite(eng.ess_streamed()[1]).any()
+        with pytest.raises(bnr.BnrError):
+            eng.ess_stream_finish()
+
+
 @pytest.mark.parametrize("shape", [(100, 7, 1000, 6, "nform"), (30, 7, 500, 6, "qform"), (40, 5, 384, 5, "nform")])
 def test_full_size_runs_are_bitwise_reproducible_across_chain_groups(bnr, shape):
     """Full-size sweeps (TMA rings, mbarrier hand-shakes, bordered Cholesky, streamed solves) are deterministic:

@@ -87,7 +87,7 @@ def _seg(p, c, name):
 
 
 def test_abi_version_and_sizes(small, bnr):
-    assert bnr.lib().bnr_version() == 102
+    assert bnr.lib().bnr_version() == 200
     eng = small["eng"]
     assert eng.injection_size() == small["lay"]["_total"]
     assert eng.injection_size(for_init=True) == O.init_layout(small["V"], small["R"])["_total"]
