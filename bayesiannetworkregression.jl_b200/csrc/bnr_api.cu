@@ -1,5 +1,6 @@
 // C ABI of libbnr (see include/bnr.h): handle life-cycle, the sweep schedule (one CUDA graph per sweep),
 // state / trace access in reference layout, streaming R-hat, and the parity-test hooks.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -23,6 +24,11 @@ static_assert(BNR_MAX_R == bnr::MAX_R, "MAX_R out of sync");
 using namespace bnr;
 
 static thread_local std::string g_err;
+// BNR_TIMING=1: wall-clock of the fixed-cost steps (create / graph build / destroy) on stderr
+static const bool g_timing = getenv("BNR_TIMING") != nullptr;
+static double wall_ms() {
+  return 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 namespace bnr { thread_local long long g_launches = 0; }
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                         \
@@ -65,17 +71,22 @@ std::vector<CacheBlock> g_cache;
 size_t g_cache_bytes = 0;
 size_t g_cache_limit = (size_t)4 << 30;
 
-void* cache_take(int device, size_t bytes) {
+// best fit: the smallest cached block of the device that holds `bytes` without wasting more than a quarter of itself
+// (+ 1 MiB); *got receives the block's true size
+void* cache_take(int device, size_t bytes, size_t* got) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
+  size_t best = g_cache.size();
   for (size_t i = 0; i < g_cache.size(); ++i)
-    if (g_cache[i].device == device && g_cache[i].bytes == bytes) {
-      void* p = g_cache[i].p;
-      g_cache_bytes -= bytes;
-      g_cache[i] = g_cache.back();
-      g_cache.pop_back();
-      return p;
-    }
-  return nullptr;
+    if (g_cache[i].device == device && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes + bytes / 4 + ((size_t)1 << 20) &&
+        (best == g_cache.size() || g_cache[i].bytes < g_cache[best].bytes))
+      best = i;
+  if (best == g_cache.size()) return nullptr;
+  void* p = g_cache[best].p;
+  *got = g_cache[best].bytes;
+  g_cache_bytes -= g_cache[best].bytes;
+  g_cache[best] = g_cache.back();
+  g_cache.pop_back();
+  return p;
 }
 void cache_give(int device, void* p, size_t bytes) {
   {
@@ -130,9 +141,10 @@ struct bnr_handle {
 };
 
 static int raw_alloc(bnr_handle* h, void** out, size_t bytes) {
-  void* p = cache_take(h->p.device, bytes);
-  if (!p) CK(cudaMalloc(&p, bytes));
-  h->allocs.push_back({p, bytes});
+  size_t got = bytes;
+  void* p = cache_take(h->p.device, bytes, &got);
+  if (!p) { CK(cudaMalloc(&p, bytes)); got = bytes; }
+  h->allocs.push_back({p, got});
   *out = p;
   return 0;
 }
@@ -154,8 +166,10 @@ static void release_alloc(bnr_handle* h, void* p) {
 struct Scratch {
   int device; void* p = nullptr; size_t bytes = 0;
   Scratch(int dev, size_t b) : device(dev), bytes((b + 255) / 256 * 256) {
-    p = cache_take(device, bytes);
-    if (!p && cudaMalloc(&p, bytes) != cudaSuccess) p = nullptr;
+    size_t got = bytes;
+    p = cache_take(device, bytes, &got);
+    if (p) bytes = got;
+    else if (cudaMalloc(&p, bytes) != cudaSuccess) p = nullptr;
   }
   ~Scratch() { if (p) cache_give(device, p, bytes); }
 };
@@ -225,7 +239,9 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
 
   bnr_handle* h = new bnr_handle();
   h->p = *p;
+  const double t0 = wall_ms();
   const int rc = create_impl(h, p, X, y);
+  if (g_timing) fprintf(stderr, "[bnr] bnr_create %.2f ms (%zu device buffers)\n", wall_ms() - t0, h->allocs.size());
   if (rc != BNR_OK) {
     const std::string msg = g_err;      // bnr_destroy must not clobber the reason
     bnr_destroy(h);
@@ -240,7 +256,7 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
 static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, const double* y) {
   if (h->p.gig_inject_len <= 0) h->p.gig_inject_len = 64;
   Dims& d = h->e.d;
-  d.n = p->n; d.V = p->V; d.R = p->R; d.C = p->num_chains;
+  d.n = p->n; d.V = p->V; d.R = p->R; d.C = p->num_chains; d.C_total = p->num_chains;
   d.q = p->V * (p->V + 1) / 2;
   // n is padded to a multiple of 128 with AT LEAST one padding row: row n of the n x n system carries the right-hand
   // side of the forward solve through the factorisation (bnr_linalg.cu); same for q in the q-form
@@ -278,6 +294,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
 
   Engine& e = h->e;
   const size_t C = d.C;
+  const double t_create0 = wall_ms();
   double *dX, *dy;
   DA(dX, (size_t)d.qp * d.np);
   DA(dy, (size_t)d.np);
@@ -286,6 +303,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
                        (size_t)d.n * sizeof(double), (size_t)d.q, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(dy, y, (size_t)d.n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   e.X = dX; e.y = dy;
+  if (g_timing) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[bnr]   X, y upload done at +%.2f ms\n", wall_ms() - t_create0); }
   std::vector<int2> lk(d.q);
   {
     int j = 0;
@@ -322,15 +340,15 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     for (int j = 0; j < d.q; ++j)
       for (int i = 0; i < d.n; ++i) xt[(size_t)i * d.qp + j] = X[(size_t)i + (size_t)d.n * j];
     double *dXT = nullptr, *dOnes = nullptr, *dXtX = nullptr;
-    CK(cudaMalloc((void**)&dXT, xt.size() * sizeof(double)));
-    CK(cudaMalloc((void**)&dOnes, ones.size() * sizeof(double)));
+    DA(dXT, xt.size());              // (tracked by the handle: released below, or by bnr_destroy on a failure path)
+    DA(dOnes, ones.size());
     DA(dXtX, (size_t)d.qp * d.qp);
     CK(cudaMemcpyAsync(dXT, xt.data(), xt.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dOnes, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     launch_xtx(d, dXT, dOnes, dXtX, h->stream);
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaFree(dXT));
-    CK(cudaFree(dOnes));
+    release_alloc(h, dXT);
+    release_alloc(h, dOnes);
     e.XtX = dXtX;
   }
   DA(e.partials, C * d.nparts * (2 * MAX_R + 1));
@@ -367,7 +385,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     // chain groups (see ChainGroup): 2 by default once there are enough chains to split
     // default: 2 groups once the SYRK of half the chains fills the GPU for several waves; 4 when the chains are few
     // (then the per-group latency chain, not the tensor pipe, bounds the sweep and more of them must overlap)
-    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 64 ? 2 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
+    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 96 ? 2 : (d.C >= 48 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1))));
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > d.C) ng = d.C;
     h->n_groups = ng;
@@ -407,6 +425,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
       DA(G.mom_window, 5);
     }
   }
+  if (g_timing) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[bnr]   buffers, streams, events at +%.2f ms\n", wall_ms() - t_create0); }
   h->tmp_doubles = (size_t)1 << 22;
   DA(h->d_tmp, h->tmp_doubles);
   e.inj = nullptr; e.inj_stride = 0;
@@ -447,6 +466,7 @@ extern "C" int bnr_set_cache_limit(int64_t bytes) {
 
 extern "C" int bnr_destroy(bnr_handle* h) {
   if (!h) return BNR_OK;
+  const double t_destroy0 = wall_ms();
   cudaSetDevice(h->p.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
@@ -470,6 +490,7 @@ extern "C" int bnr_destroy(bnr_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  if (g_timing) fprintf(stderr, "[bnr] bnr_destroy %.2f ms\n", wall_ms() - t_destroy0);
   return BNR_OK;
 }
 
@@ -582,6 +603,7 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
 // on the whole chain set.
 static int build_graphs(bnr_handle* h) {
   if (h->graphs_ready) return BNR_OK;
+  const double t0 = wall_ms();
   const long long before = g_launches;
   const int C = h->e.d.C, ng = h->n_groups;
   for (int g = 0; g < ng; ++g) {
@@ -599,6 +621,7 @@ static int build_graphs(bnr_handle* h) {
   }
   h->graph_kernels = g_launches - before;
   h->graphs_ready = true;
+  if (g_timing) fprintf(stderr, "[bnr] graph capture + instantiate (%d groups, %lld kernels) %.2f ms\n", ng, h->graph_kernels, wall_ms() - t0);
   return BNR_OK;
 }
 
@@ -669,6 +692,7 @@ extern "C" int bnr_sync(bnr_handle* h) {
 
 extern "C" int bnr_last_run_ms(bnr_handle* h, float* ms) {
   if (!h || !ms || !h->ran) return fail(BNR_ESTATE, "no run recorded");
+  CK(cudaSetDevice(h->p.device));
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return BNR_OK;
@@ -676,6 +700,7 @@ extern "C" int bnr_last_run_ms(bnr_handle* h, float* ms) {
 
 extern "C" int bnr_iteration(bnr_handle* h, int64_t* completed) {
   if (!h || !completed) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   long long v = 0;
   CK(cudaMemcpyAsync(&v, h->e.iter, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -685,6 +710,7 @@ extern "C" int bnr_iteration(bnr_handle* h, int64_t* completed) {
 
 extern "C" int bnr_set_trace_row(bnr_handle* h, int64_t row) {
   if (!h || row < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   long long v = row;
   CK(cudaMemcpyAsync(h->e.trace_row, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -693,6 +719,7 @@ extern "C" int bnr_set_trace_row(bnr_handle* h, int64_t row) {
 
 extern "C" int bnr_get_trace_row(bnr_handle* h, int64_t* row) {
   if (!h || !row) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   long long v = 0;
   CK(cudaMemcpyAsync(&v, h->e.trace_row, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -702,24 +729,25 @@ extern "C" int bnr_get_trace_row(bnr_handle* h, int64_t* row) {
 
 extern "C" int bnr_copy_trace_rows(bnr_handle* h, int64_t dst, int64_t src, int64_t count) {
   if (!h || dst < 0 || src < 0 || count < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   if (dst + count > e.trace_rows || src + count > e.trace_rows) return fail(BNR_EINVAL, "rows out of range");
   if (count == 0 || dst == src) return BNR_OK;
-  // rows are contiguous per chain; regions may overlap -> stage through a temporary when they do
+  // rows are contiguous per chain; regions may overlap -> stage through one temporary (stream order keeps the chains apart)
+  const bool overlap = !(dst + count <= src || src + count <= dst);
+  const size_t max_row = (size_t)(e.tr_full ? e.rowlen_full : 0) > (size_t)(e.d.V + e.d.q) ? (size_t)e.rowlen_full
+                                                                                           : (size_t)(e.d.V + e.d.q);
+  Scratch sc(h->p.device, overlap ? (size_t)count * max_row * sizeof(double) : 256);
+  if (overlap && !sc.p) return fail(BNR_ENOMEM, "device scratch allocation failed");
   auto move = [&](double* base, size_t rowlen, int chains) -> int {
     for (int c = 0; c < chains; ++c) {
       double* b = base + (size_t)c * e.trace_rows * rowlen;
       const size_t bytes = (size_t)count * rowlen * sizeof(double);
-      const bool overlap = !(dst + count <= src || src + count <= dst);
       if (!overlap) {
         CK(cudaMemcpyAsync(b + (size_t)dst * rowlen, b + (size_t)src * rowlen, bytes, cudaMemcpyDeviceToDevice, h->stream));
       } else {
-        void* tmp = nullptr;
-        CK(cudaMalloc(&tmp, bytes));
-        CK(cudaMemcpyAsync(tmp, b + (size_t)src * rowlen, bytes, cudaMemcpyDeviceToDevice, h->stream));
-        CK(cudaMemcpyAsync(b + (size_t)dst * rowlen, tmp, bytes, cudaMemcpyDeviceToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaFree(tmp));
+        CK(cudaMemcpyAsync(sc.p, b + (size_t)src * rowlen, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(b + (size_t)dst * rowlen, sc.p, bytes, cudaMemcpyDeviceToDevice, h->stream));
       }
     }
     return 0;
@@ -741,6 +769,7 @@ static int push_windows(bnr_handle* h) {
 
 extern "C" int bnr_set_moment_window(bnr_handle* h, int64_t first, int64_t len) {
   if (!h || len < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   h->win[0] = first; h->win[1] = len;
   int r = push_windows(h);
   if (r) return r;
@@ -789,6 +818,7 @@ __global__ void k_merge_blocks(const double* __restrict__ bmom, int nb_cap, int 
 
 extern "C" int bnr_moments_from_blocks(bnr_handle* h, int32_t first_block, int32_t nblocks) {
   if (!h || first_block < 0 || nblocks < 2 || (nblocks & 1)) return fail(BNR_EINVAL, "need an even number of blocks >= 2");
+  CK(cudaSetDevice(h->p.device));
   if (!h->e.bmom || first_block + nblocks > (int)h->win[4]) return fail(BNR_ESTATE, "blocks not configured (bnr_set_moment_blocks)");
   const Dims& d = h->e.d;
   const int np_ = d.V + d.q;
@@ -802,6 +832,7 @@ extern "C" int bnr_moments_from_blocks(bnr_handle* h, int32_t first_block, int32
 
 extern "C" int bnr_moments_device(bnr_handle* h, double** dev_ptr, int64_t* count) {
   if (!h || !dev_ptr || !count) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   CK(cudaStreamSynchronize(h->stream));
   *dev_ptr = h->e.moments;
   *count = (int64_t)h->e.d.C * 2 * (h->e.d.V + h->e.d.q) * 2;
@@ -844,6 +875,7 @@ __global__ void k_moments_from_trace(const double* __restrict__ tr, long long tr
 
 extern "C" int bnr_moments_from_trace(bnr_handle* h, int64_t first_row, int64_t nrows) {
   if (!h || first_row < 0 || nrows < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   if (!e.tr_gx || e.trace_gx_chains < e.d.C)
     return fail(BNR_ESTATE, "gamma/xi traces of every chain are needed (trace_gamma_xi_all = 0): use the streaming "
@@ -861,12 +893,14 @@ extern "C" int bnr_moments_from_trace(bnr_handle* h, int64_t first_row, int64_t 
 
 extern "C" int bnr_moment_half_len(bnr_handle* h, int64_t* half_len) {
   if (!h || !half_len) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   *half_len = h->mom_half;
   return BNR_OK;
 }
 
 extern "C" int bnr_rhat(bnr_handle* h, double* rhat_xi, double* rhat_gamma) {
   if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
   if (h->mom_half < 2) return fail(BNR_ESTATE, "moment window too short for R-hat");
   const Dims& d = h->e.d;
   launch_rhat(h->e.moments, d.C, d.V + d.q, h->mom_half, h->d_rhat, h->stream);
@@ -880,6 +914,7 @@ extern "C" int bnr_rhat(bnr_handle* h, double* rhat_xi, double* rhat_gamma) {
 
 extern "C" int bnr_var_size(bnr_handle* h, int32_t var, int64_t* n) {
   if (!h || !n || var < 0 || var >= BNR_NUM_VARS) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   *n = var_size(h->e.d, var);
   return BNR_OK;
 }
@@ -905,6 +940,7 @@ static double* var_ptr(Engine& e, int c, int var) {
 extern "C" int bnr_get_state(bnr_handle* h, int32_t chain, int32_t var, double* out) {
   if (!h || !out || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS)
     return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   const int n = var_size(h->e.d, var), R = h->e.d.R;
   std::vector<double> tmp(n);
   CK(cudaMemcpyAsync(tmp.data(), var_ptr(h->e, chain, var), sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -921,6 +957,7 @@ extern "C" int bnr_get_state(bnr_handle* h, int32_t chain, int32_t var, double* 
 extern "C" int bnr_set_state(bnr_handle* h, int32_t chain, int32_t var, const double* in) {
   if (!h || !in || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS)
     return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   const int n = var_size(h->e.d, var), R = h->e.d.R;
   std::vector<double> tmp(in, in + n);
   if (var == BNR_VAR_PI)
@@ -947,6 +984,7 @@ __global__ void k_gather_trace(const double* __restrict__ rows, size_t rowlen, i
 extern "C" int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t first, int64_t last, double* out) {
   if (!h || !out || chain < 0 || chain >= h->e.d.C || var < 0 || var >= BNR_NUM_VARS || first < 0 || last < first)
     return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   if (last > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
   const Dims& d = e.d;
@@ -987,6 +1025,7 @@ extern "C" int bnr_get_trace(bnr_handle* h, int32_t chain, int32_t var, int64_t 
 
 extern "C" int bnr_status(bnr_handle* h, int32_t* status) {
   if (!h || !status) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   CK(cudaMemcpyAsync(status, h->e.status, sizeof(int) * h->e.d.C, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return BNR_OK;
@@ -997,6 +1036,7 @@ extern "C" int bnr_status(bnr_handle* h, int32_t* status) {
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int bnr_injection_size(bnr_handle* h, int32_t for_init, int64_t* per_chain) {
   if (!h || !per_chain) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   const Dims& d = h->e.d;
   *per_chain = for_init ? InitLayout::make(d.V, d.R).total : InjLayout::make(d.n, d.V, d.R, d.gigK).total;
   return BNR_OK;
@@ -1004,6 +1044,7 @@ extern "C" int bnr_injection_size(bnr_handle* h, int32_t for_init, int64_t* per_
 
 extern "C" int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_chain) {
   if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
   CK(cudaStreamSynchronize(h->stream));
   drop_graph(h);
   if (!inj) { h->e.inj = nullptr; h->e.inj_stride = 0; return BNR_OK; }
@@ -1025,6 +1066,7 @@ extern "C" int bnr_set_injection(bnr_handle* h, const double* inj, int64_t per_c
 
 extern "C" int bnr_enable_aux(bnr_handle* h, int32_t on) {
   if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   const Dims& d = e.d;
   const size_t C = d.C;
@@ -1052,6 +1094,7 @@ extern "C" int bnr_enable_aux(bnr_handle* h, int32_t on) {
 
 extern "C" int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double* out, int64_t capacity) {
   if (!h || !out || chain < 0 || chain >= h->e.d.C) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   if (!h->aux_on) return fail(BNR_ESTATE, "call bnr_enable_aux first");
   Engine& e = h->e;
   const Dims& d = e.d;
@@ -1148,6 +1191,7 @@ extern "C" int bnr_step(bnr_handle* h, int32_t cond) {
 
 extern "C" int bnr_finish_sweep(bnr_handle* h) {
   if (!h) return fail(BNR_EINVAL, "null handle");
+  CK(cudaSetDevice(h->p.device));
   launch_record(h->e, 1, h->stream);
   if (h->e.ess_ring) launch_ess_stream(h->e, h->stream);
   launch_advance(h->e, 1, h->stream);
@@ -1156,9 +1200,29 @@ extern "C" int bnr_finish_sweep(bnr_handle* h) {
   return BNR_OK;
 }
 
+// the jitter ladder of update_u_xi! (src/gibbs.jl:322-347) on a caller-supplied R x R matrix (col-major host arrays)
+extern "C" int bnr_test_chol_jitter(bnr_handle* h, int32_t R, const double* A, double* A_used, double* L, int32_t* status) {
+  if (!h || !A || !A_used || !L || !status || R < 1 || R > BNR_MAX_R) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
+  const size_t RR = (size_t)R * R;
+  if (3 * RR + 1 > h->tmp_doubles) return fail(BNR_EINVAL, "staging buffer too small");
+  double* d = h->d_tmp;
+  CK(cudaMemcpyAsync(d, A, sizeof(double) * RR, cudaMemcpyHostToDevice, h->stream));
+  launch_test_chol_jitter(R, d, d + RR, d + 2 * RR, reinterpret_cast<int*>(d + 3 * RR), h->stream);
+  CK(cudaMemcpyAsync(A_used, d + RR, sizeof(double) * RR, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(L, d + 2 * RR, sizeof(double) * RR, cudaMemcpyDeviceToHost, h->stream));
+  int st = 0;
+  CK(cudaMemcpyAsync(&st, d + 3 * RR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  *status = st;
+  return BNR_OK;
+}
+
 static int rng_dump(bnr_handle* h, int chain, int64_t iteration, int site, int element, int kind, double shape,
                     int count, double* out) {
   if (!h || !out || count < 1 || chain < 0 || chain >= h->e.d.C) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   if ((size_t)count > h->tmp_doubles) return fail(BNR_EINVAL, "count too large");
   launch_rng_dump(h->e.d, chain, iteration, site, element, kind, shape, count, h->d_tmp, h->stream);
   CK(cudaMemcpyAsync(out, h->d_tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
@@ -1185,6 +1249,7 @@ extern "C" int bnr_summary(bnr_handle* h, int32_t chain, int64_t first_row, int6
                            int64_t rank_hi, double* gamma_mean, double* gamma_lo, double* gamma_hi, double* xi_mean) {
   if (!h || chain < 0 || chain >= h->e.d.C || first_row < 0 || nrows < 1)
     return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   const Dims& d = e.d;
   if (first_row + nrows > e.trace_rows) return fail(BNR_EINVAL, "rows beyond trace capacity");
@@ -1225,6 +1290,7 @@ extern "C" int bnr_summary(bnr_handle* h, int32_t chain, int64_t first_row, int6
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t max_lag) {
   if (!h || first_row < 0 || nrows < 4 || max_lag < 1) return fail(BNR_EINVAL, "bad arguments (need nrows >= 4, max_lag >= 1)");
+  CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
   const Dims& d = e.d;
   if (!e.tr_gx || e.trace_gx_chains < d.C)
@@ -1257,7 +1323,7 @@ extern "C" int bnr_ess_accumulate(bnr_handle* h, int64_t first_row, int64_t nrow
 
 // Streaming variant: the next `ndraws` sweeps contribute their lagged products while they run (k_ess_stream), so no
 // chain needs a trace.  bnr_ess_stream_finish turns the accumulators into the same two statistics buffers.
-extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndraws) {
+static int ess_stream_arm(bnr_handle* h, int32_t max_lag, int64_t first_sweep, int64_t ndraws) {
   if (!h || ndraws < 4 || max_lag < 1) return fail(BNR_EINVAL, "bad arguments (need ndraws >= 4, max_lag >= 1)");
   CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
@@ -1268,7 +1334,12 @@ extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndra
   const int L = max_lag, cap = L + 8;
   const size_t P = (size_t)d.V + d.q, C = d.C;
   CK(cudaStreamSynchronize(h->stream));
-  drop_graph(h);                         // the sweep graphs gain (or keep) the k_ess_stream node and its pointers
+  long long it = 0;
+  CK(cudaMemcpyAsync(&it, e.iter, sizeof(it), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (first_sweep < 0) first_sweep = it + 1;
+  if (first_sweep <= it) return fail(BNR_EINVAL, "the window must start after the sweeps already run");
+  if (!e.ess_ring || e.ess_L != L) drop_graph(h);   // the sweep graphs gain the k_ess_stream node / its new geometry
   const size_t need = C * P * ((size_t)cap + L + (L + 1) + 2);
   if (need > h->ess_stream_cap) {
     void* pnew = nullptr;
@@ -1278,6 +1349,7 @@ extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndra
     if (r) return r;
     h->ess_stream_cap = need;
     h->ess_stream_buf = (double*)pnew;
+    drop_graph(h);
   }
   e.ess_ring = h->ess_stream_buf;
   e.ess_head = e.ess_ring + C * P * cap;
@@ -1285,10 +1357,7 @@ extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndra
   e.ess_sum = e.ess_acc + C * P * (L + 1);
   e.ess_L = L; e.ess_cap = cap;
   e.ess_win = h->d_esswin;
-  long long it = 0;
-  CK(cudaMemcpyAsync(&it, e.iter, sizeof(it), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  const long long win[4] = {it + 1, ndraws, L, cap};
+  const long long win[4] = {first_sweep, ndraws, L, cap};
   CK(cudaMemcpyAsync(h->d_esswin, win, sizeof(win), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   const size_t acov_need = (size_t)(L + 1) * P;
@@ -1305,6 +1374,17 @@ extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndra
   h->ess_stream_N = ndraws;
   h->ess_lag = -1;
   return BNR_OK;
+}
+
+// Streaming variant: the next `ndraws` sweeps contribute their lagged products while they run (k_ess_stream), so no
+// chain needs a trace.  bnr_ess_stream_finish turns the accumulators into the same two statistics buffers.
+extern "C" int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndraws) {
+  return ess_stream_arm(h, max_lag, -1, ndraws);
+}
+
+extern "C" int bnr_ess_stream_window(bnr_handle* h, int32_t max_lag, int64_t first_sweep, int64_t ndraws) {
+  if (first_sweep < 1) return fail(BNR_EINVAL, "first_sweep is a 1-based sweep number");
+  return ess_stream_arm(h, max_lag, first_sweep, ndraws);
 }
 
 extern "C" int bnr_ess_stream_finish(bnr_handle* h) {
@@ -1332,6 +1412,7 @@ extern "C" int bnr_ess_stream_finish(bnr_handle* h) {
 extern "C" int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov, double** chain_mean,
                               int64_t* n_mean, int32_t* max_lag) {
   if (!h || !acov_sum || !n_acov || !chain_mean || !n_mean || !max_lag) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   if (h->ess_lag < 0) return fail(BNR_ESTATE, "call bnr_ess_accumulate first");
   const int P = h->e.d.V + h->e.d.q;
   *acov_sum = h->d_acov; *n_acov = (int64_t)(h->ess_lag + 1) * P;
@@ -1342,6 +1423,7 @@ extern "C" int bnr_ess_device(bnr_handle* h, double** acov_sum, int64_t* n_acov,
 
 extern "C" int bnr_export_ess(bnr_handle* h, double* dev_acov_dst, double* dev_means_dst) {
   if (!h || !dev_acov_dst || !dev_means_dst) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   if (h->ess_lag < 0) return fail(BNR_ESTATE, "call bnr_ess_accumulate first");
   const size_t P = (size_t)h->e.d.V + h->e.d.q;
   CK(cudaMemcpyAsync(dev_acov_dst, h->d_acov, sizeof(double) * (h->ess_lag + 1) * P, cudaMemcpyDeviceToDevice, h->stream));
@@ -1388,24 +1470,35 @@ extern "C" int bnr_ess(bnr_handle* h, int64_t first_row, int64_t nrows, int32_t 
 
 extern "C" int bnr_gamma_mode(bnr_handle* h, int32_t* mode) {
   if (!h || !mode) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   *mode = h->e.d.gmode;
+  return BNR_OK;
+}
+
+extern "C" int bnr_device_copy(int device, void* dev_dst, const void* dev_src, int64_t bytes) {
+  if (!dev_dst || !dev_src || bytes < 0) return fail(BNR_EINVAL, "bad arguments");
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpy(dev_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToDevice));
   return BNR_OK;
 }
 
 extern "C" int bnr_chain_groups(bnr_handle* h, int32_t* groups) {
   if (!h || !groups) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   *groups = h->n_groups;
   return BNR_OK;
 }
 
 extern "C" int bnr_launch_count(bnr_handle* h, int64_t* kernels) {
   if (!h || !kernels) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   *kernels = h->launches;
   return BNR_OK;
 }
 
 extern "C" int bnr_export_moments(bnr_handle* h, double* dev_dst) {
   if (!h || !dev_dst) return fail(BNR_EINVAL, "null argument");
+  CK(cudaSetDevice(h->p.device));
   const size_t n = (size_t)h->e.d.C * 2 * (h->e.d.V + h->e.d.q) * 2;
   CK(cudaMemcpyAsync(dev_dst, h->e.moments, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));

@@ -14,6 +14,8 @@ constexpr int PART_BLOCK = 256;  // threads per block of the edge kernels (parti
 
 struct Dims {
   int n, V, R, q, C;
+  int C_total;        // chains of the whole handle (C is the count of the view: a chain group sees a part); schedule
+                      // choices that change the rounding depend on C_total only, so chain groups never change results
   int np, qp;         // padded n (multiple of TILE_N) and q (multiple of TILE_K; of TILE_N in the q-form)
   int gmode;          // gamma draw: 1 = n x n Bhattacharya form (G = X D X' + I), 2 = q x q precision form
   int gdim;           // dimension of the matrix that is factored every sweep: np (n-form) or qp (q-form); always

@@ -32,6 +32,7 @@ void launch_init(const Engine& e, cudaStream_t s);
 void launch_record(const Engine& e, int sweep_done, cudaStream_t s);
 void launch_advance(const Engine& e, int inc_iter, cudaStream_t s);
 void launch_rhat(const double* mom, int chains, int nparams, long long h, double* out, cudaStream_t s);
+void launch_test_chol_jitter(int R, const double* Ain, double* Aused, double* Lout, int* status, cudaStream_t s);
 void launch_rng_dump(const Dims& d, int chain, long long iteration, int site, int element, int kind, double shape,
                      int count, double* out, cudaStream_t s);
 

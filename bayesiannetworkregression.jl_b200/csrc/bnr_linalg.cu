@@ -21,6 +21,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy (TMA engine) helpers
@@ -268,7 +272,8 @@ template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
           size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
-          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0, int part = 0) {
+          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0, int part = 0,
+          int nstrip = 1) {
   extern __shared__ __align__(16) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
@@ -295,11 +300,17 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   } else {
     // MODE 1 (Cholesky update of block column jb = origin) and MODE 2 (panel solve of block column jb): the CTAs of a
     // launch cover the row blocks part, part + 1, ... of that column (part >= jb; part == jb includes the diagonal tile)
+    // When the launch has too few tiles to occupy the GPU (few chains: the latency-bound regime) every tile is cut
+    // into nstrip (2 or 4) row strips of 128 / nstrip rows, one CTA each: the same fragments in the same k order
+    // (bit-identical results), a quarter of the DMMA chain per CTA.  A diagonal tile is then computed like any other
+    // (its upper triangle is written too; nobody reads it).
     jb = origin;
-    ib = part + blockIdx.y;
+    ib = part + (int)blockIdx.y / nstrip;
   }
-  const int i0 = ib * SY_BT, j0 = jb * SY_BT;
-  const bool diag = (ib == jb);
+  const int strip = (MODE == 0) ? 0 : (int)blockIdx.y % nstrip;
+  const int rows_i = SY_BT / nstrip;
+  const int i0 = ib * SY_BT + strip * rows_i, j0 = jb * SY_BT;
+  const bool diag = (ib == jb) && nstrip == 1;
   const double* Ac = A + (size_t)c * a_chain_stride;
   const double* sc = (MODE == 0) ? scale + (size_t)c * scale_stride : nullptr;
   // operand sources (k-major: element (row, k) at base[row + ld * k]).  MODE 0 / 1: both operands are row blocks of
@@ -319,7 +330,7 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     // ---------------- producer warpgroup: hands its registers to the consumers, one lane drives the TMA engine ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SY_PRODUCER_REGS));
     if (warp == 8 && lane == 0) {
-      const unsigned bytes = (diag ? 1u : 2u) * SY_BK * SY_BT * 8u + (MODE == 0 ? SY_BK * 8u : 0u);
+      const unsigned bytes = SY_BK * SY_BT * 8u + (diag ? 0u : SY_BK * (unsigned)rows_i * 8u) + (MODE == 0 ? SY_BK * 8u : 0u);
       for (int kt = 0; kt < nk; ++kt) {
         const int stage = kt % SY_STAGES;
         const unsigned ph = (kt / SY_STAGES) & 1;
@@ -332,7 +343,7 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
 #pragma unroll 4
         for (int kr = 0; kr < SY_BK; ++kr) {
           bulk_g2s(sj + kr * SY_LDS, gj + (size_t)kr * ldj, SY_BT * 8, &full[stage]);
-          if (!diag) bulk_g2s(si + kr * SY_LDS, gi + (size_t)kr * ld, SY_BT * 8, &full[stage]);
+          if (!diag) bulk_g2s(si + kr * SY_LDS, gi + (size_t)kr * ld, rows_i * 8, &full[stage]);
         }
         if (MODE == 0) bulk_g2s(si + SY_BK * SY_LDS, sc + kt * SY_BK, SY_BK * 8, &full[stage]);
       }
@@ -363,7 +374,7 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   // Rows >= nvalid are zero padding: their entries of C are exactly zero, were zero-initialised at allocation and
   // are never written by any kernel, so skipping them changes nothing.
   int nfv = (nvalid - i0 + 7) / 8;
-  nfv = nfv > 16 ? 16 : nfv;
+  nfv = nfv > rows_i / 8 ? rows_i / 8 : nfv;
   if (nfv <= 0) {
     // the whole row block is padding: keep the stage hand-shake alive and leave
     for (int kt = 0; kt < nk; ++kt) {
@@ -426,17 +437,17 @@ __global__ void __launch_bounds__(256) k_syrk_splitk_reduce(double* __restrict__
 // launch applies any contiguous range of panels.
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
-              int nk, int jb, int ib_first) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, nullptr, 0, ib_first);
+              int nk, int jb, int ib_first, int nstrip) {
+  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, nullptr, 0, ib_first, nstrip);
 }
 
 // panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I = ib_first, ... (in place: a CTA
 // has consumed its whole tile through the ring before the first store)
 __global__ void __launch_bounds__(SY_THREADS, 1)
 k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int jb, int ib_first,
-            const double* __restrict__ Linv, size_t linv_chain_stride) {
+            const double* __restrict__ Linv, size_t linv_chain_stride, int nstrip) {
   syrk_body<2>(G, chain_stride, np, nullptr, 0, G, chain_stride, np, nvalid, SY_BT / SY_BK, jb, 0.0, Linv,
-               linv_chain_stride, ib_first);
+               linv_chain_stride, ib_first, nstrip);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -459,7 +470,7 @@ k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int
 //     shared-memory ring, 64-column half blocks), every step is a block mat-vec; the diagonal blocks use Linv.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;            // panel / diagonal block size
-constexpr int CHOL_MAX_DIM = 4096; // largest factored dimension (shared-memory solution vector of the back solve)
+constexpr int CHOL_MAX_DIM = 8192; // largest factored dimension (the back solve keeps the solution vector in shared memory)
 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
@@ -517,9 +528,41 @@ __device__ __forceinline__ void frag_mm32(double& c0, double& c1, const double* 
   }
 }
 
+// NF independent fragments at once, k outermost: the NF accumulator chains interleave, so the warp is bound by the DMMA
+// issue rate instead of the latency of one dependent chain (8 DMMAs back to back)
+template <int NF>
+__device__ __forceinline__ void frag_mm32_batch(double (&c)[NF][2], const double* const (&Aop)[NF], const int (&lda)[NF],
+                                                const double* const (&Bop)[NF], const int (&ldb)[NF],
+                                                const int (&m0)[NF], const int (&n0)[NF], int lk, int lr) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    const int k = k4 * 4 + lk;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const double bt = Bop[i][(n0[i] + lr) * ldb[i] + k];
+      const double at = Aop[i][k * lda[i] + m0[i] + lr];
+      dmma884(c[i][0], c[i][1], bt, at);
+    }
+  }
+}
+
 constexpr int PLD = 132;           // column stride of the 128 x 128 working block (== 4 mod 16: conflict-free fragments)
 constexpr int XD_LD = 36;          // column stride of the 32 x 32 scratch blocks (== 4 mod 16)
 constexpr int XD_BLK = 32 * XD_LD;
+// Optional in-kernel time stamps (lab builds only, -DBNR_POTF2_STAMPS): thread 0 of chain 0 records globaltimer at the
+// phase boundaries of k_potf2_inv into bnr::g_potf2_stamps.
+#ifdef BNR_POTF2_STAMPS
+__device__ unsigned long long g_potf2_stamps[64];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+#define STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_potf2_stamps[i] = gtimer(); } while (0)
+#else
+#define STAMP(i) do { } while (0)
+#endif
+
 constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB + 64) + 32;
 constexpr int PU_ROWS = 32;        // k-rows of L(J, J-1) per staged chunk of the in-kernel diagonal update
 static_assert(2 * PU_ROWS * PLD <= 8 * XD_BLK, "the update ring aliases the inverse scratch");
@@ -576,16 +619,22 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   const int lk = lane & 3, lr = lane >> 2;
   double* Gc = G + (size_t)c * chain_stride;
   double* D = Gc + (size_t)J * PB * N + (size_t)J * PB;
+  STAMP(0);
   if (tid == 0) {
     mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  if (warp == 0) {
-    if (lane == 0) mbar_expect_tx(&bar[0], PB * PB * 8);
-    __syncwarp();
-#pragma unroll
-    for (int col = lane; col < PB; col += 32) bulk_g2s(A + col * PLD, D + (size_t)col * N, PB * 8, &bar[0]);
+  // the 128 x 128 block: 16-byte LDGSTS copies by all threads (a 1 KB column = one coalesced request of 64 threads;
+  // 128 one-kilobyte bulk copies took 4.4 us here -- the TMA engine accepts ~1 such request per 30 ns)
+  {
+    const int chunk = tid & 63, c0 = tid >> 6;
+#pragma unroll 8
+    for (int i = 0; i < PB / 4; ++i) {
+      const int col = c0 + 4 * i;
+      cp_async16(A + col * PLD + chunk * 2, D + (size_t)col * N + chunk * 2);
+    }
+    cp_async_commit();
   }
   if (late && J > 0) {
     // L[J, J-1]: rows J*128.., columns (J-1)*128..: element (row, k) at Lp[row + N * k]
@@ -620,7 +669,8 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
         if (warp == 1) issue(chunk + 2);
       }
     }
-    mbar_wait(&bar[0], 0);
+    cp_async_wait<0>();
+    __syncthreads();
     switch (warp) {
       case 0: potf2_update_apply<0>(A, lk, lr, acc); break;
       case 1: potf2_update_apply<1>(A, lk, lr, acc); break;
@@ -633,8 +683,10 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
     }
     __syncthreads();
   } else {
-    mbar_wait(&bar[0], 0);
+    cp_async_wait<0>();
+    __syncthreads();
   }
+  STAMP(1);
   bool bad = false;
   for (int s = 0; s < PB / 32; ++s) {
     const int o = s * 32;
@@ -672,13 +724,18 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
         if (lane >= j) A[(o + j) * PLD + o + lane] = a[j];
     }
     __syncthreads();
-    // rows below: x L_ss' = a, thread per row, right-looking (independent FMAs, broadcast reads of L_ss)
+    STAMP(2 + 3 * s);
+    // rows below: x L_ss' = a, thread per row, right-looking (independent FMAs, broadcast reads of L_ss).  Warp 7 runs the
+    // SAME code on the 32 unit rows e_j: x = e_j L_ss^-T is column j of L_ss^-1, so the inverse of the diagonal block
+    // (needed for Linv below) costs no extra phase -- and no extra code: this straight-line solve runs cold from the
+    // instruction cache (~10 cycles per instruction), a separate copy of it for the inverses took 7 us per panel.
     const int nbelow = PB - (o + 32);
-    if (tid < nbelow) {
+    const bool inv_row = (warp == 7);
+    if (tid < nbelow || inv_row) {
       double* row = A + o * PLD + o + 32 + tid;
       double x[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = row[j * PLD];
+      for (int j = 0; j < 32; ++j) x[j] = inv_row ? ((j == lane) ? 1.0 : 0.0) : row[j * PLD];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const double xj = x[j] * dall[o + j];
@@ -686,10 +743,16 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
 #pragma unroll
         for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PLD + o + k];
       }
+      if (inv_row) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) row[j * PLD] = x[j];
+        for (int j = 0; j < 32; ++j) Xd[s * XD_BLK + lane * XD_LD + j] = (j >= lane) ? x[j] : 0.0;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) row[j * PLD] = x[j];
+      }
     }
     __syncthreads();
+    STAMP(3 + 3 * s);
     // trailing update on the tensor cores: A[r][cc] -= sum_p L[r][o+p] L[cc][o+p] for o+32 <= cc <= r, by 8 x 8
     // fragments of the lower triangle (diagonal fragments are computed whole; what lands above the diagonal is
     // never read).  Fragment (fr, fc), fc <= fr; the warps take them round-robin.
@@ -713,35 +776,24 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
       }
     }
     __syncthreads();
+    STAMP(4 + 3 * s);
   }
   if (bad) atomicOr(&status[c], BNR_ST_G_NOTPD_);
-  // the factor goes back to global memory (full columns: the part above the diagonal is never read by anyone)
-  fence_async_smem();
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int col = lane; col < PB; col += 32) bulk_s2g(D + (size_t)col * N, A + col * PLD, PB * 8);
-    bulk_commit();
-    bulk_wait_read0();
-  }
-  // ---- inverse, in place ----
-  // (1) the four 32 x 32 diagonal inverses, thread per column: x = e_j, forward substitution in registers
-  if (tid < 128) {
-    const int b = tid >> 5, j = tid & 31, o = 32 * b;
-    double x[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const double xk = x[k] * dall[o + k];
-      x[k] = xk;
-#pragma unroll
-      for (int i = k + 1; i < 32; ++i) x[i] -= A[(o + k) * PLD + o + i] * xk;
+  // the factor goes back to global memory (full columns: the part above the diagonal is never read by anyone), 16 bytes
+  // per thread and store
+  {
+    const int chunk = tid & 63, c0 = tid >> 6;
+#pragma unroll 8
+    for (int i = 0; i < PB / 4; ++i) {
+      const int col = c0 + 4 * i;
+      *reinterpret_cast<double2*>(D + (size_t)col * N + chunk * 2) = *reinterpret_cast<const double2*>(A + col * PLD + chunk * 2);
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) Xd[b * XD_BLK + j * XD_LD + i] = (i >= j) ? x[i] : 0.0;
   }
-  __syncthreads();   // also orders the bulk-store reads (tid 0 waited above) before the in-place overwrite below
+  STAMP(14);
+  // ---- inverse, in place ----
+  // (1) the four 32 x 32 diagonal inverses were computed next to the factorisation (warp 7 of the "rows below" pass)
+  __syncthreads();
+  STAMP(15);
   // (2) off-diagonal 32 x 32 blocks of the inverse by the recursive 2 x 2 block formula
   //        [[A, 0], [C, B]]^-1 = [[A^-1, 0], [-B^-1 C A^-1, B^-1]],
   //     first inside the two 64 x 64 diagonal blocks, then for the 64 x 64 block below them: four stages of 32^3
@@ -750,153 +802,221 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   auto put = [&](double* Cb, int ldc, int m0, int n0, double c0, double c1) {
     *reinterpret_cast<double2*>(Cb + (n0 + lr) * ldc + m0 + 2 * lk) = make_double2(c0, c1);
   };
-  // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1        (32 fragments, 4 per warp)
-  for (int t = warp; t < 32; t += 8) {
-    const int b = t >> 4, m0 = ((t >> 2) & 3) * 8, n0 = (t & 3) * 8;
-    double c0 = 0.0, c1 = 0.0;
-    frag_mm32(c0, c1, blkA(2 * b + 1, 2 * b), PLD, Xd + (2 * b) * XD_BLK, XD_LD, m0, n0, lk, lr);
-    put(Tm + b * XD_BLK, XD_LD, m0, n0, c0, c1);
+  // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1        (32 fragments, 4 per warp, computed together)
+  {
+    double c4[4][2];
+    const double* Ap[4]; const double* Bp[4];
+    int la[4], lb[4], m0[4], n0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = warp + 8 * i, b = t >> 4;
+      m0[i] = ((t >> 2) & 3) * 8; n0[i] = (t & 3) * 8;
+      Ap[i] = blkA(2 * b + 1, 2 * b); la[i] = PLD; Bp[i] = Xd + (2 * b) * XD_BLK; lb[i] = XD_LD;
+      c4[i][0] = c4[i][1] = 0.0;
+    }
+    frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) put(Tm + ((warp + 8 * i) >> 4) * XD_BLK, XD_LD, m0[i], n0[i], c4[i][0], c4[i][1]);
   }
   __syncthreads();
   // stage 2: X_(2b+1, 2b) = -Xd_(2b+1) T_b
-  for (int t = warp; t < 32; t += 8) {
-    const int b = t >> 4, m0 = ((t >> 2) & 3) * 8, n0 = (t & 3) * 8;
-    double c0 = 0.0, c1 = 0.0;
-    frag_mm32(c0, c1, Xd + (2 * b + 1) * XD_BLK, XD_LD, Tm + b * XD_BLK, XD_LD, m0, n0, lk, lr);
-    put(blkA(2 * b + 1, 2 * b), PLD, m0, n0, -c0, -c1);
+  {
+    double c4[4][2];
+    const double* Ap[4]; const double* Bp[4];
+    int la[4], lb[4], m0[4], n0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = warp + 8 * i, b = t >> 4;
+      m0[i] = ((t >> 2) & 3) * 8; n0[i] = (t & 3) * 8;
+      Ap[i] = Xd + (2 * b + 1) * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + b * XD_BLK; lb[i] = XD_LD;
+      c4[i][0] = c4[i][1] = 0.0;
+    }
+    frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = (warp + 8 * i) >> 4;
+      put(blkA(2 * b + 1, 2 * b), PLD, m0[i], n0[i], -c4[i][0], -c4[i][1]);
+    }
   }
   __syncthreads();
   // stage 3: T2 = C A^-1 with C = blocks (2..3, 0..1):  T2_(i,0) = C_(i,0) X_00 + C_(i,1) X_10,  T2_(i,1) = C_(i,1) X_11
-  //          (64 fragments; every warp takes two fragment positions in each of the four blocks -> equal work)
-  for (int t = warp; t < 64; t += 8) {
-    const int blk = (t >> 3) & 3, fpos = ((t >> 5) << 3) | (t & 7), ib = blk >> 1, jb = blk & 1, i = 2 + ib;
-    const int m0 = (fpos >> 2) * 8, n0 = (fpos & 3) * 8;
-    double c0 = 0.0, c1 = 0.0;
-    if (jb == 0) {
-      frag_mm32(c0, c1, blkA(i, 0), PLD, Xd, XD_LD, m0, n0, lk, lr);
-      frag_mm32(c0, c1, blkA(i, 1), PLD, blkA(1, 0), PLD, m0, n0, lk, lr);
-    } else {
-      frag_mm32(c0, c1, blkA(i, 1), PLD, Xd + XD_BLK, XD_LD, m0, n0, lk, lr);
-    }
-    put(Tm + (2 * ib + jb) * XD_BLK, XD_LD, m0, n0, c0, c1);
-  }
-  __syncthreads();
+  //          (64 fragments; every warp takes two fragment positions in each of the four blocks -> equal work;
+  //           the 8 fragments of a warp run as two batches of 4 independent chains, the second product of the
+  //           left-column blocks as a third)
   // stage 4: X_C = -B^-1 T2:  X_(2,j) = -X_22 T2_(2,j),  X_(3,j) = -(X_32 T2_(2,j) + X_33 T2_(3,j)), j = 0, 1
-  for (int t = warp; t < 64; t += 8) {
-    const int blk = (t >> 3) & 3, fpos = ((t >> 5) << 3) | (t & 7), ib = blk >> 1, jb = blk & 1;
-    const int m0 = (fpos >> 2) * 8, n0 = (fpos & 3) * 8;
-    double c0 = 0.0, c1 = 0.0;
-    if (ib == 0) {
-      frag_mm32(c0, c1, Xd + 2 * XD_BLK, XD_LD, Tm + jb * XD_BLK, XD_LD, m0, n0, lk, lr);
-    } else {
-      frag_mm32(c0, c1, blkA(3, 2), PLD, Tm + jb * XD_BLK, XD_LD, m0, n0, lk, lr);
-      frag_mm32(c0, c1, Xd + 3 * XD_BLK, XD_LD, Tm + (2 + jb) * XD_BLK, XD_LD, m0, n0, lk, lr);
-    }
-    put(blkA(2 + ib, jb), PLD, m0, n0, -c0, -c1);
-  }
-  __syncthreads();
-  // (3) diagonal blocks from Xd, exact zeros above the diagonal (the panel solve sums over all 128 k)
-  for (int id = tid; id < PB * PB; id += 256) {
-    const int r = id & (PB - 1), cc = id >> 7;
-    if (r < cc) A[cc * PLD + r] = 0.0;
-    else if ((r >> 5) == (cc >> 5)) A[cc * PLD + r] = Xd[(r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31)];
-  }
-  fence_async_smem();
-  __syncthreads();
-  if (warp == 0) {
-    double* dst = Linv + ((size_t)c * T + J) * PB * PB;
 #pragma unroll
-    for (int col = lane; col < PB; col += 32) bulk_s2g(dst + col * PB, A + col * PLD, PB * 8);
-    bulk_commit();
-    bulk_wait0();
+  for (int stage = 3; stage <= 4; ++stage) {
+    double c8[8][2];
+    int m8[8], n8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = warp + 8 * i, fpos = ((t >> 5) << 3) | (t & 7);
+      m8[i] = (fpos >> 2) * 8; n8[i] = (fpos & 3) * 8;
+      c8[i][0] = c8[i][1] = 0.0;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double c4[4][2];
+      const double* Ap[4]; const double* Bp[4];
+      int la[4], lb[4], m0[4], n0[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = 4 * half + i, t = warp + 8 * ii, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
+        m0[i] = m8[ii]; n0[i] = n8[ii];
+        c4[i][0] = c4[i][1] = 0.0;
+        if (stage == 3) {
+          if (jb == 0) { Ap[i] = blkA(2 + ib, 0); la[i] = PLD; Bp[i] = Xd; lb[i] = XD_LD; }
+          else { Ap[i] = blkA(2 + ib, 1); la[i] = PLD; Bp[i] = Xd + XD_BLK; lb[i] = XD_LD; }
+        } else {
+          if (ib == 0) { Ap[i] = Xd + 2 * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + jb * XD_BLK; lb[i] = XD_LD; }
+          else { Ap[i] = blkA(3, 2); la[i] = PLD; Bp[i] = Tm + jb * XD_BLK; lb[i] = XD_LD; }
+        }
+      }
+      frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { c8[4 * half + i][0] = c4[i][0]; c8[4 * half + i][1] = c4[i][1]; }
+    }
+    {
+      // second products: stage 3, left-column blocks (jb == 0): += C_(i,1) X_10; stage 4, bottom blocks (ib == 1):
+      // += X_33 T2_(3,j).  With t = warp + 8 i: blk = i & 3, so jb == 0 <=> i even, ib == 1 <=> (i & 2) != 0.
+      double c4[4][2];
+      const double* Ap[4]; const double* Bp[4];
+      int la[4], lb[4], m0[4], n0[4], idx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = (stage == 3) ? 2 * i : (4 * (i >> 1) + 2 + (i & 1));
+        const int t = warp + 8 * ii, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
+        idx[i] = ii; m0[i] = m8[ii]; n0[i] = n8[ii];
+        c4[i][0] = c8[ii][0]; c4[i][1] = c8[ii][1];
+        if (stage == 3) { Ap[i] = blkA(2 + ib, 1); la[i] = PLD; Bp[i] = blkA(1, 0); lb[i] = PLD; }
+        else { Ap[i] = Xd + 3 * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + (2 + jb) * XD_BLK; lb[i] = XD_LD; }
+      }
+      frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { c8[idx[i]][0] = c4[i][0]; c8[idx[i]][1] = c4[i][1]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = warp + 8 * i, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
+      if (stage == 3) put(Tm + (2 * ib + jb) * XD_BLK, XD_LD, m8[i], n8[i], c8[i][0], c8[i][1]);
+      else put(blkA(2 + ib, jb), PLD, m8[i], n8[i], -c8[i][0], -c8[i][1]);
+    }
+    __syncthreads();
   }
+  STAMP(16);
+  // (3) Linv_J goes to global memory straight from the pieces: the diagonal 32 x 32 blocks from Xd, the blocks below them
+  //     from A, exact zeros above the diagonal (the panel solve sums over all 128 k)
+  {
+    double* dst = Linv + ((size_t)c * T + J) * PB * PB;
+    const int chunk = tid & 63, c0 = tid >> 6, r = chunk * 2;
+#pragma unroll 8
+    for (int i = 0; i < PB / 4; ++i) {
+      const int cc = c0 + 4 * i;
+      double2 v;
+      if ((r >> 5) == (cc >> 5)) {
+        const double* xd = Xd + (r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31);
+        v.x = (r >= cc) ? xd[0] : 0.0;
+        v.y = (r + 1 >= cc) ? xd[1] : 0.0;
+      } else if (r > cc) {
+        v = *reinterpret_cast<const double2*>(A + cc * PLD + r);
+      } else {
+        v.x = 0.0; v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(dst + (size_t)cc * PB + r) = v;
+    }
+  }
+  STAMP(17);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward solve  L' x = b,  b = w (+ addz), w = row m of the factor (see above).  One CTA per chain; a producer
-// warp streams the factor once, bottom-right to top-left, as 64-column half blocks (64 bulk copies of 1 KB) into a
-// ring; 8 consumer warps turn every half block into 64 dot products (warp per 8 columns, lanes over the rows):
+// backward solve  L' x = b,  b = w (+ addz), w = row m of the factor (see above).  One CTA per chain streams the factor
+// once, bottom-right to top-left, in parts of BW_COLS columns x 128 rows through a multi-stage cp.async ring: every
+// thread issues 16-byte LDGSTS copies (a 1 KB column is one coalesced request of 64 threads).  The first version fed
+// the ring with 1 KB bulk copies from a producer warp; the TMA engine accepts only about one such request per 30 ns,
+// which capped the solve at ~30 GB/s per CTA (157 us for a 1024 x 1024 factor).  8 warps turn every part into BW_COLS
+// dot products (warp per BW_COLS / 8 columns, lanes over the rows):
 //   off-diagonal block (I, J): b_J -= L[I, J]' x_I          diagonal block J: x_J = Linv_J' b_J
-// grid = C, block = 288 (8 consumer warps + 1 producer warp).
+// grid = C, block = 256.
 // ------------------------------------------------------------------------------------------------------------
 #ifndef BNR_BW_COLS
-#define BNR_BW_COLS 64
+#define BNR_BW_COLS 32
 #endif
 constexpr int BW_COLS = BNR_BW_COLS;             // columns per staged part of a 128 x 128 block
 constexpr int BW_NH = PB / BW_COLS;              // parts per block
-constexpr int BW_CPW = BW_COLS / 8;              // columns per consumer warp
-constexpr int BW_MAX_STAGES = (192 / BW_COLS) < 8 ? (192 / BW_COLS) : 8;   // at most 192 KB of ring, 8 barriers
+constexpr int BW_CPW = BW_COLS / 8;              // columns per warp
+constexpr int BW_MAX_STAGES = 6;
 constexpr int BW_STAGE_DBL = BW_COLS * PB;
 static int bwd_stages(int N) {
   const size_t budget = 227 * 1024 - sizeof(double) * (size_t)N - 256;
   int ns = (int)(budget / (sizeof(double) * BW_STAGE_DBL));
   return ns > BW_MAX_STAGES ? BW_MAX_STAGES : ns;
 }
-static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 160; }
+static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 64; }
 
-__global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G, size_t chain_stride, int N, int m,
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {      // wait until at most n groups are pending (n < 6)
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    default: cp_async_wait<4>(); break;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bwd_stream(const double* __restrict__ G, size_t chain_stride, int N, int m,
                                                     const double* __restrict__ Linv, double* __restrict__ out,
                                                     int out_stride, const double* __restrict__ addz, int addz_stride,
                                                     int nstages) {
   extern __shared__ __align__(16) double sm[];
   double* ring = sm;
   double* x = sm + (size_t)nstages * BW_STAGE_DBL;     // [N] right-hand side, overwritten block by block by x
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(x + N);
-  unsigned long long* empty = full + 8;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = N / PB;
   const double* Gc = G + (size_t)c * chain_stride;
   const double* Lc = Linv + (size_t)c * T * PB * PB;
-  if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
+  const int total = T * (T + 1) / 2 * BW_NH;
+
+  // producer state: the part that is issued next, in consumption order (J down, I from T-1 down to J, h up)
+  int pJ = T - 1, pI = T - 1, ph = 0, issued = 0;
+  auto issue = [&]() {
+    if (issued < total) {
+      double* dst = ring + (size_t)(issued % nstages) * BW_STAGE_DBL;
+      const bool dg = (pI == pJ);
+      const double* src = dg ? Lc + (size_t)pJ * PB * PB + (size_t)ph * BW_COLS * PB
+                             : Gc + (size_t)(pJ * PB + ph * BW_COLS) * N + (size_t)pI * PB;
+      const size_t cs = dg ? PB : N;
+      const int chunk = tid & 63, c0 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < BW_COLS / 4; ++i) {
+        const int col = c0 + 4 * i;
+        cp_async16(dst + col * PB + chunk * 2, src + (size_t)col * cs + chunk * 2);
+      }
+      ++issued;
+      if (++ph == BW_NH) { ph = 0; if (--pI < pJ) { --pJ; pI = T - 1; } }
+    }
+    cp_async_commit();                                 // (an empty group keeps the group count in step)
+  };
+  for (int s = 0; s < nstages - 1; ++s) issue();
   for (int k = tid; k < N; k += blockDim.x)
     x[k] = (k < m) ? Gc[(size_t)k * N + m] + (addz ? addz[(size_t)c * addz_stride + k] : 0.0) : 0.0;
-  __syncthreads();
-
-  if (warp == 8) {
-    // lane 0 owns the hand-shake; the 32 lanes then issue the 64 bulk copies of the stage two each (a single lane
-    // needs longer to issue them than the consumers need to use them)
-    int it = 0;
-    for (int J = T - 1; J >= 0; --J)
-      for (int I = T - 1; I >= J; --I)            // I == J: the diagonal block, taken from Linv, comes last
-        for (int h = 0; h < BW_NH; ++h, ++it) {
-          const int stage = it % nstages;
-          double* dst = ring + (size_t)stage * BW_STAGE_DBL;
-          if (lane == 0) {
-            mbar_wait(&empty[stage], ((it / nstages) & 1) ^ 1);
-            mbar_expect_tx(&full[stage], BW_STAGE_DBL * 8);
-          }
-          __syncwarp();
-          const double* src = (I == J) ? Lc + (size_t)J * PB * PB + (size_t)h * BW_COLS * PB
-                                       : Gc + (size_t)(J * PB + h * BW_COLS) * N + (size_t)I * PB;
-          const size_t cs = (I == J) ? PB : N;
-#pragma unroll
-          for (int col = lane; col < BW_COLS; col += 32) bulk_g2s(dst + col * PB, src + col * cs, PB * 8, &full[stage]);
-        }
-    return;
-  }
 
   int it = 0;
   double xn[BW_NH][BW_CPW];                          // diagonal-block results of this warp's columns (all parts)
   for (int J = T - 1; J >= 0; --J) {
     for (int I = T - 1; I >= J; --I) {
       const bool dg = (I == J);
-      if (dg) asm volatile("bar.sync 1, 256;\n" ::: "memory");     // b_J complete (all warps' updates landed)
-      const double* v = x + I * PB;
-      const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
 #pragma unroll
       for (int h = 0; h < BW_NH; ++h, ++it) {
-        const int stage = it % nstages;
-        mbar_wait(&full[stage], (it / nstages) & 1);
-        const double* B = ring + (size_t)stage * BW_STAGE_DBL + (size_t)(warp * BW_CPW) * PB + lane;
+        cp_async_wait_dyn(nstages - 2);              // this thread's copies of part `it` have landed
+        __syncthreads();                             // ... everybody's; part it-1 is consumed; b / x updates visible
+        issue();                                     // refill the buffer part it-1 occupied
+        const double* v = x + I * PB;
+        const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+        const double* B = ring + (size_t)(it % nstages) * BW_STAGE_DBL + (size_t)(warp * BW_CPW) * PB + lane;
         double acc[BW_CPW];
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q)
           acc[q] = B[q * PB] * v0 + B[q * PB + 32] * v1 + B[q * PB + 64] * v2 + B[q * PB + 96] * v3;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q) {
 #pragma unroll
@@ -912,15 +1032,16 @@ __global__ void __launch_bounds__(288) k_bwd_stream(const double* __restrict__ G
         }
       }
     }
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");               // everybody has read b_J
+    __syncthreads();                                 // everybody has read b_J
     if (lane == 0) {
 #pragma unroll
       for (int h = 0; h < BW_NH; ++h)
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q) x[J * PB + h * BW_COLS + warp * BW_CPW + q] = xn[h][q];
     }
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");               // x_J visible to the next block column
+    // (x_J becomes visible to the other warps at the __syncthreads of the next part)
   }
+  __syncthreads();
   for (int k = tid; k < N; k += 256) out[(size_t)c * out_stride + k] = x[k];
 }
 
@@ -1107,7 +1228,8 @@ int syrk_splits(const Dims& d, int C) {
     if (s > nk / 8) s = nk / 8;
     return s < 1 ? 1 : (s > SYRK_MAX_SPLITS ? SYRK_MAX_SPLITS : s);
   }
-  if (tiles * C >= 4 * 148) return 1;
+  // (measured: once chains x tiles reaches one wave, splitting only removes the natural stagger between chain groups)
+  if (tiles * C >= 148) return 1;
   int s = (4 * 148 + tiles * C - 1) / (tiles * C);
   if (s > nk / 24) s = nk / 24;
   if (s > SYRK_MAX_SPLITS) s = SYRK_MAX_SPLITS;
@@ -1187,19 +1309,29 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
 }
 
 // Factor every G_c (gdim x gdim) in place; the forward solve L w = rhs rides along as row m of the matrix.
-// Schedule: left-looking with a one-panel lookahead, so that the latency-bound chain is as short as it can be with one
-// kernel per step.  Per panel J, in program order (every tile sees its updates in this order on any schedule):
-//   PA(J)      k_potf2_inv    D_JJ -= L[J,J-1] L[J,J-1]' (late part, in the kernel), factor, invert       [main]
-//   T1(J)      k_trsm_dmma    tile (J+1, J)                                                               [main]
-//   T2(J)      k_trsm_dmma    tiles (i, J), i >= J+2                                                      [side]
-//   Ulate(J)   k_chol_update  tiles (i, J+1), i >= J+2, contribution of panel J only (depth 128)          [side]
-//   Uearly(J)  k_chol_update  tiles (i, J+2), i >= J+2 (diagonal included), panels 0..J (depth 128 (J+1)) [side]
-// i.e. block column j receives the panels 0..j-2 early (as soon as they exist, off the critical path) and panel j-1
-// late.  The critical path per panel is PA + T1; everything else runs on `side` (a forked branch of the graph) next to
-// the following panel factorisation, which occupies at most one SM per chain.
-//   dependencies across the two streams:  T2(J) after PA(J);  Ulate(J) after T1(J);
-//                                         T1(J+1) after Ulate(J);  PA(J+2) after Uearly(J).
-// Without a side stream the same kernels run in program order on `s` (identical results).
+// Two schedules of the same blocked algorithm, chosen from the handle's chain count (never from the chain grouping):
+//
+// (A) throughput schedule -- many chains, the SMs are busy anyway and total SM time is what counts.  Left-looking, one
+//     deep update per block column; per panel J:
+//       k_chol_update  tile (J, J) and, on `side`, tiles (i, J), i > J: all panels 0..J-1 at once (depth 128 J)
+//       k_potf2_inv    factor + invert the diagonal block                                                  [main]
+//       k_trsm_dmma    tiles (i, J), i > J                                                                 [main]
+//
+// (B) latency schedule -- few chains (chains x (T-1) <= 64), the GPU is mostly idle and the length of the dependent
+//     chain is what counts.  Left-looking with a one-panel look-ahead; per panel J, in program order (every tile sees its
+//     updates in this order on any schedule):
+//       PA(J)      k_potf2_inv    D_JJ -= L[J,J-1] L[J,J-1]' (late part, in the kernel), factor, invert       [main]
+//       T1(J)      k_trsm_dmma    tile (J+1, J)                                                               [main]
+//       T2(J)      k_trsm_dmma    tiles (i, J), i >= J+2                                                      [side]
+//       Ulate(J)   k_chol_update  tiles (i, J+1), i >= J+2, contribution of panel J only (depth 128)          [side]
+//       Uearly(J)  k_chol_update  tiles (i, J+2), i >= J+2 (diagonal included), panels 0..J (depth 128 (J+1)) [side]
+//     i.e. block column j receives the panels 0..j-2 early (as soon as they exist, off the critical path) and panel j-1
+//     late.  The critical path per panel is PA + T1; everything else runs on `side` next to the following panel
+//     factorisation.  Tiles are cut into row strips (syrk_body) while the launch stays within one wave of CTAs.
+//       dependencies across the two streams:  T2(J) after PA(J);  Ulate(J) after T1(J);
+//                                             T1(J+1) after Ulate(J);  PA(J+2) after Uearly(J).
+// `side` is a forked branch of the graph with the priority of the main stream.  Without a side stream the same kernels
+// run in program order on `s` (identical results).
 void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStream_t s) {
   const Dims& d = e.d;
   const int N = d.gdim;
@@ -1208,13 +1340,54 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
   const int T = N / PB;
   const size_t ls = (size_t)T * PB * PB;
   static const bool serial = getenv("BNR_CHOL_SERIAL") != nullptr;        // debugging knob: program order on one stream
+  static const int forced = getenv("BNR_CHOL_SCHEDULE") ? atoi(getenv("BNR_CHOL_SCHEDULE")) : 0;   // 1 = (A), 2 = (B)
+  const bool latency = forced ? forced == 2 : (long long)d.C_total * (T - 1) <= 64;
+  ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
+
+  if (!latency) {
+    // ---- (A) ----
+    const bool can_fork = !serial && fj.side != nullptr;
+    for (int J = 0; J < T; ++J) {
+      const bool fork = can_fork && J > 0 && J + 1 < T;
+      if (J > 0) {
+        const int nk = J * PB / SY_BK;
+        if (fork) {
+          cudaEventRecord(fj.fork, s);
+          cudaStreamWaitEvent(fj.side, fj.fork, 0);
+          dim3 g2(d.C, T - J - 1);
+          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, fj.side>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J + 1, 1);
+          cudaEventRecord(fj.join, fj.side);
+          dim3 g1(d.C, 1);
+          ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J, 1);
+        } else {
+          dim3 g2(d.C, T - J);
+          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J, 1);
+        }
+      }
+      ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status, 0);
+      if (fork) cudaStreamWaitEvent(s, fj.join, 0);
+      if (J + 1 < T) {
+        dim3 g1(d.C, T - J - 1);
+        ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls, 1);
+      }
+    }
+    return;
+  }
+
+  // ---- (B) ----
   const bool fork = !serial && fj.side_hi != nullptr && fj.pool != nullptr && fj.npool >= 4 * T;
   cudaStream_t side = fork ? fj.side_hi : s;
   cudaEvent_t* evP = fj.pool;                       // [T] each: after PA, after T1, after Ulate, after Uearly
   cudaEvent_t* evT = fj.pool + T;
   cudaEvent_t* evL = fj.pool + 2 * T;
   cudaEvent_t* evE = fj.pool + 3 * T;
-  ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
+  // row strips per tile (see syrk_body): as many as keep the launch within one wave of CTAs
+  auto strips = [&](int tiles) {
+    static const int fs = getenv("BNR_STRIPS") ? atoi(getenv("BNR_STRIPS")) : 0;      // tuning knob (1, 2 or 4)
+    if (fs == 1 || fs == 2 || fs == 4) return fs;
+    const int ctas = d.C_total * tiles;
+    return ctas * 4 <= 148 ? 4 : (ctas * 2 <= 148 ? 2 : 1);
+  };
   for (int J = 0; J < T; ++J) {
     const bool has_side = J + 2 < T;
     if (fork && J >= 2) cudaStreamWaitEvent(s, evE[J - 2], 0);
@@ -1222,21 +1395,23 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
     if (fork && has_side) cudaEventRecord(evP[J], s);
     if (J + 1 < T) {
       if (fork && J >= 1 && J + 1 < T) cudaStreamWaitEvent(s, evL[J - 1], 0);
-      dim3 g1(d.C, 1);
-      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls);
+      const int ns1 = strips(1);
+      dim3 g1(d.C, ns1);
+      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls, ns1);
       if (fork && has_side) cudaEventRecord(evT[J], s);
     }
     if (has_side) {
       const int rows = T - J - 2;                   // row blocks J+2 .. T-1
       if (fork) cudaStreamWaitEvent(side, evP[J], 0);
-      dim3 g2(d.C, rows);
-      ++g_launches; k_trsm_dmma<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, m + 1, J, J + 2, e.Linv + (size_t)J * PB * PB, ls);
+      const int ns2 = strips(rows);
+      dim3 g2(d.C, rows * ns2);
+      ++g_launches; k_trsm_dmma<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, m + 1, J, J + 2, e.Linv + (size_t)J * PB * PB, ls, ns2);
       if (fork) cudaStreamWaitEvent(side, evT[J], 0);
       ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1,
-                                                                   PB / SY_BK, J + 1, J + 2);
+                                                                   PB / SY_BK, J + 1, J + 2, ns2);
       if (fork) cudaEventRecord(evL[J], side);
       ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, e.G, N, m + 1, (J + 1) * PB / SY_BK,
-                                                                   J + 2, J + 2);
+                                                                   J + 2, J + 2, ns2);
       if (fork) cudaEventRecord(evE[J], side);
     }
   }
@@ -1248,7 +1423,7 @@ void launch_chol_solve(const Engine& e, double* out, const double* addz, cudaStr
   const int N = d.gdim;
   const int m = d.gmode == 2 ? d.q : d.n;
   const int stride = d.gmode == 2 ? d.qp : d.np;
-  ++g_launches; k_bwd_stream<<<d.C, 288, bwd_smem(N), s>>>(e.G, (size_t)N * N, N, m, e.Linv, out, stride, addz, stride,
+  ++g_launches; k_bwd_stream<<<d.C, 256, bwd_smem(N), s>>>(e.G, (size_t)N * N, N, m, e.Linv, out, stride, addz, stride,
                                                         bwd_stages(N));
 }
 

@@ -66,6 +66,55 @@ __device__ bool warp_chol(double* A, int R, int lane) {
   return ok;
 }
 
+// Cholesky of a small SPD matrix with the reference's jitter ladder (src/gibbs.jl:322-347: on failure add 1e-5 I and
+// retry, on a second failure a further 4e-5 I, then give up), by one warp.  In: A (col-major R x R, shared memory).
+// Out: A = the Cholesky factor of the matrix that finally factored, A0 = that matrix; returns BNR_ST_JITTER_ /
+// BNR_ST_SIGMA_NOTPD_ bits.
+__device__ int warp_chol_ladder(double* A, double* A0, int R, int lane) {
+  const int RR = R * R;
+  int status = 0;
+  for (int i = lane; i < RR; i += 32) A0[i] = A[i];
+  __syncwarp();
+  bool ok = warp_chol(A, R, lane);
+  if (!ok) {
+    status |= BNR_ST_JITTER_;
+    if (lane < R) A0[lane + R * lane] += 1e-5;
+    __syncwarp();
+    for (int i = lane; i < RR; i += 32) A[i] = A0[i];
+    __syncwarp();
+    ok = warp_chol(A, R, lane);
+    if (!ok) {
+      if (lane < R) A0[lane + R * lane] += 4e-5;
+      __syncwarp();
+      for (int i = lane; i < RR; i += 32) A[i] = A0[i];
+      __syncwarp();
+      ok = warp_chol(A, R, lane);
+      if (!ok) status |= BNR_ST_SIGMA_NOTPD_;
+    }
+  }
+  return status;
+}
+
+// parity-test hook for the ladder alone (bnr_test_chol_jitter): one warp, matrix in / factor + used matrix + status out
+__global__ void k_test_chol_jitter(int R, const double* __restrict__ Ain, double* __restrict__ Aused,
+                                   double* __restrict__ Lout, int* __restrict__ status) {
+  __shared__ double A[MAX_R * MAX_R], A0[MAX_R * MAX_R];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < R * R; i += 32) A[i] = Ain[i];
+  __syncwarp();
+  const int st = warp_chol_ladder(A, A0, R, lane);
+  __syncwarp();
+  for (int i = lane; i < R * R; i += 32) {
+    Aused[i] = A0[i];
+    Lout[i] = (i % R >= i / R) ? A[i] : 0.0;
+  }
+  if (lane == 0) *status = st;
+}
+
+void launch_test_chol_jitter(int R, const double* Ain, double* Aused, double* Lout, int* status, cudaStream_t s) {
+  k_test_chol_jitter<<<1, 32, 0, s>>>(R, Ain, Aused, Lout, status);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // tau^2  (update_tau2!, src/gibbs.jl:267-277): InverseGamma(n/2 + q/2, 1/2 |y - mu - X gamma|^2 + 1/2 sum (gamma-W)^2/S)
 // grid = (nb, C), block = 256: the two sums are split over nb = tau2_blocks(q) blocks per chain; the last block to
@@ -223,25 +272,7 @@ __global__ void __launch_bounds__(32 * UXI_WARPS) k_uxi(Engine e) {
   // by the whole warp; the O(R^2) solves and the sequential draws stay with lane 0
   int status = 0;
   if (misc[1] == 0.0) status |= BNR_ST_SIGMA_NOTPD_;
-  for (int i = lane; i < RR; i += 32) A0[i] = A[i];
-  __syncwarp();
-  bool ok = warp_chol(A, R, lane);
-  if (!ok) {
-    status |= BNR_ST_JITTER_;
-    if (lane < R) A0[lane + R * lane] += 1e-5;
-    __syncwarp();
-    for (int i = lane; i < RR; i += 32) A[i] = A0[i];
-    __syncwarp();
-    ok = warp_chol(A, R, lane);
-    if (!ok) {
-      if (lane < R) A0[lane + R * lane] += 4e-5;
-      __syncwarp();
-      for (int i = lane; i < RR; i += 32) A[i] = A0[i];
-      __syncwarp();
-      ok = warp_chol(A, R, lane);
-      if (!ok) status |= BNR_ST_SIGMA_NOTPD_;
-    }
-  }
+  status |= warp_chol_ladder(A, A0, R, lane);
   if (lane == 0) {
     // mu_t = Sigma b : solve L w = b, L' mu_t = w
     double ldA = 0.0;

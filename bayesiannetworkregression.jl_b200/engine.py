@@ -305,6 +305,15 @@ class Engine:
         check(self._L.bnr_get_aux(self._h, int(chain), AUX[name], _dp(out), size))
         return out
 
+    def test_chol_jitter(self, A):
+        """(matrix that factored, lower factor, status bits) of the device's Cholesky-with-jitter ladder."""
+        A = np.asfortranarray(A, dtype=np.float64)
+        R = A.shape[0]
+        used, L = np.empty(R * R), np.empty(R * R)
+        st = C.c_int32()
+        check(self._L.bnr_test_chol_jitter(self._h, R, _dp(A), _dp(used), _dp(L), C.byref(st)))
+        return used.reshape((R, R), order="F"), L.reshape((R, R), order="F"), int(st.value)
+
     def rng_stream(self, chain, iteration, site, element, kind, count):
         out = np.empty(count)
         check(self._L.bnr_rng_stream(self._h, chain, iteration, site, element, {"uniform": 0, "normal": 1}[kind],

@@ -1,16 +1,20 @@
 """Host side of `Fit!` / `Summary` (src/gibbs.jl:725-751, 897-1020, 1051-1198, 1214-1250).
 
-Only orchestration lives here: keyword handling, parameters.log, X vectorisation (setup_X!), the row
-bookkeeping of run! (purge_burn ring), the PSRF-driven "extend burn-in" and "doubling" control loops and the
-Summary tables.  Every Gibbs iteration, the traces and the R-hat reduction run on the GPU inside libbnr.
+Only argument handling lives here: keyword names, parameters.log, X vectorisation (setup_X!), wrapping the returned
+buffers as Results and the Summary tables.  The chain generation -- every Gibbs iteration, the row bookkeeping of run!
+(purge_burn ring), both PSRF-driven control loops, the R-hat reduction and the Summary statistics -- is ONE call into
+libbnr (bnr_fit, csrc/bnr_fit.cu), so a Julia `ccall` wrapper is equally thin (julia/BNRB200.jl).
 """
+import ctypes as C
 import datetime
 import math
 import random
 
 import numpy as np
 
-from .engine import Engine
+from .capi import lib, check, check_fit, FitParams, FitInfo, ALLGATHER_FN, STATE, VAR, GAMMA_MODE
+
+_DP = C.POINTER(C.c_double)
 
 _UNI = {"tau2": "τ²", "u": "u", "xi": "ξ", "gamma": "γ", "S": "S", "theta": "θ", "Delta": "Δ", "M": "M",
         "mu": "μ", "lam": "λ", "pi": "πᵥ"}
@@ -121,25 +125,6 @@ def _citation():
             "journal = {In preparation}\n}")
 
 
-# -- run! : the row bookkeeping of src/gibbs.jl:849-864 turned into device run segments -----------------
-def _run_rows(eng, first_index, nburn, total, purge_burn):
-    """Generate rows exactly as run! would (1-based first_index/total, ring on purge_burn during burn-in)."""
-    j = first_index
-    seg_start, seg_len = j, 0
-    for i in range(first_index, total + 1):
-        seg_len += 1
-        if purge_burn is not None and i < nburn and j == purge_burn + 1:
-            eng.trace_row = seg_start - 1
-            eng.run(seg_len)
-            eng.copy_trace_rows(0, j - 1, 1)      # copy_table!(state, 1, j)
-            j = 1
-            seg_start, seg_len = 2, 0
-        j += 1
-    if seg_len:
-        eng.trace_row = seg_start - 1
-        eng.run(seg_len)
-
-
 def _dist_world():
     """(rank, world) of an initialised torch.distributed process group, else (0, 1).  One process per GPU: every rank
     calls Fit with its own share of the chains (the reference spreads chains over Distributed.jl workers,
@@ -153,84 +138,120 @@ def _dist_world():
     return 0, 1
 
 
-def _psrf(eng, nb, nsamp, streamed=False):
-    """return_psrf_VOI (src/gibbs.jl:771-789): R-hat over table rows nb+1 .. nb+nsamp of every chain.
-    streamed: the split-half moments of exactly those draws were accumulated while the chains ran
-    (bnr_set_moment_window), so no chain but the first needs a trace.
-    In a torch.distributed job the per-rank moments ([chain][half][param][mean, M2], 32 (V+q) bytes per chain -- the
-    only data that crosses NVLink) are all-gathered and every rank reduces them in the same order, so all ranks take
-    the same PSRF decisions."""
-    if nsamp // 2 < 2:
-        return np.full(eng.V, np.nan), np.full(eng.q, np.nan)
-    if not streamed:
-        eng.moments_from_trace(nb, nsamp)
+def _torch_allgather(ctx, device, send, recv, count):
+    """bnr_allgather_fn for a torch.distributed job: the per-rank moments ([chain][half][param][mean, M2], 32 (V+q)
+    bytes per chain -- the only data that crosses NVLink) are all-gathered over NCCL (or on the host with gloo, for the
+    CPU-side rendezvous of the tests); every rank then reduces them in the same order inside libbnr."""
+    try:
+        import torch
+        import torch.distributed as dist
+        L = lib()
+        dev = torch.device("cuda", device)
+        world = dist.get_world_size()
+        mine = torch.empty(count, dtype=torch.float64, device=dev)
+        check(L.bnr_device_copy(device, C.c_void_p(mine.data_ptr()), C.c_void_p(send), count * 8))
+        if dist.get_backend() == "nccl":
+            allm = torch.empty(count * world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allm, mine)
+        else:
+            host = torch.empty(count * world, dtype=torch.float64)
+            dist.all_gather_into_tensor(host, mine.cpu())
+            allm = host.to(dev)
+        torch.cuda.synchronize(dev)
+        check(L.bnr_device_copy(device, C.c_void_p(recv), C.c_void_p(allm.data_ptr()), count * world * 8))
+        return 0
+    except Exception:                                   # an exception must not unwind through the C frames
+        import traceback
+        traceback.print_exc()
+        return 1
+
+
+_ALLGATHER = ALLGATHER_FN(_torch_allgather)
+
+
+def _native_fit(Xn, y, R, *, eta, zeta, iota, a_delta, b_delta, nu, nburn=0, nsamp=0, mingen=0, maxgen=0,
+                psrf_cutoff=1.01, purge_burn=None, num_chains=2, seed=0, device=0, return_state="full", verbose=False,
+                chain_offset=0, n_devices=1, ess_max_lag=0, interval=95, gamma_mode="auto", chain_groups=0):
+    """One bnr_fit call (include/bnr.h): chain generation, purge ring, PSRF loop, R-hat, Summary statistics on the GPU."""
+    L = lib()
+    Xf = np.asfortranarray(Xn, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n, q = Xf.shape
+    V = int(round((-1 + math.sqrt(1 + 8 * q)) / 2))
+    if V * (V + 1) // 2 != q:
+        raise ValueError("q = %d is not V(V+1)/2 for an integer V" % q)
+    p = FitParams()
+    L.bnr_fit_default_params(C.byref(p))
+    b = p.base
+    b.n, b.V, b.R, b.num_chains, b.chain_offset, b.device = n, V, int(R), int(num_chains), int(chain_offset), int(device)
+    b.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    b.eta, b.zeta, b.iota, b.a_delta, b.b_delta, b.nu = eta, zeta, iota, a_delta, b_delta, float(nu)
+    b.gamma_mode = GAMMA_MODE[gamma_mode] if isinstance(gamma_mode, str) else int(gamma_mode)
+    b.chain_groups = int(chain_groups)
+    p.nburn, p.nsamples, p.mingen, p.maxgen = int(nburn), int(nsamp), int(mingen), int(maxgen)
+    p.psrf_cutoff = float(psrf_cutoff)
+    p.purge_burn = int(purge_burn) if purge_burn else 0
+    p.return_state = STATE[return_state]
+    p.n_devices, p.interval, p.ess_max_lag, p.verbose = int(n_devices), int(interval), int(ess_max_lag), 1 if verbose else 0
     rank, world = _dist_world()
-    if world == 1:
-        return eng.rhat()
-    import torch
-    import torch.distributed as dist
-    dev = torch.device("cuda", eng.device)
-    _, cnt = eng.moments_device()
-    mine = torch.empty(cnt, dtype=torch.float64, device=dev)
-    eng.export_moments(mine.data_ptr())
-    if dist.get_backend() == "nccl":
-        allm = torch.empty(cnt * world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(allm, mine)
-    else:                                   # gloo (tests, CPU-side rendezvous): gather on the host
-        host = torch.empty(cnt * world, dtype=torch.float64)
-        dist.all_gather_into_tensor(host, mine.cpu())
-        allm = host.to(dev)
-    torch.cuda.synchronize(dev)
-    return eng.rhat_from_moments(allm.data_ptr(), eng.C * world, eng.moment_half_len())
-
-
-def _stream_last(eng, new_sweeps, nsamp):
-    """Arm the streaming moments for the last nsamp of the next `new_sweeps` sweeps (the rows the PSRF will use)."""
-    s_end = eng.iteration + new_sweeps
-    eng.set_moment_window(s_end - nsamp + 1, nsamp)
-
-
-def _fetch_state(eng, rows, what):
-    st = Table()
-    if what == "none":
-        return st
-    names = list(_UNI) if what == "full" else ["xi", "gamma"]
-    for k in names:
-        st[k] = eng.get_trace(0, k, 0, rows)
-    return st
-
-
-def _summary_ranks(nsamp, interval):
-    """lw / hi of src/gibbs.jl:1221-1223 (Julia round = ties to even, 1-based indices)."""
-    lower = (100 - interval) / 200.0
-    return _jround(nsamp * lower), _jround(nsamp * (1.0 - lower))
-
-
-def _device_summary(eng, nb, nsamp, interval=95):
-    """Summary statistics of chain 1 computed on the GPU from the device traces (bnr_summary): no nsamp x q
-    device-to-host copy and no host sort.  None when nsamp is too small for the interval (the reference raises
-    a BoundsError inside Summary, not inside Fit!)."""
-    lw, hi = _summary_ranks(nsamp, interval)
-    if lw < 1 or hi > nsamp:
-        return None
-    gm, gl, gh, xm = eng.summary(0, nb, nsamp, lw, hi)
-    return dict(interval=interval, mean=gm, lower=gl, upper=gh, xi_mean=xm, V=eng.V, q=eng.q)
-
-
-def _max(a):
-    return np.max(a) if len(a) else -np.inf   # NaN propagates like Julia's max(...)
+    if world > 1:
+        p.ext_world, p.ext_rank, p.allgather = world, rank, _ALLGATHER
+    res = C.c_void_p()
+    check_fit(L.bnr_fit(C.byref(p), Xf.ctypes.data_as(_DP), y.ctypes.data_as(_DP), C.byref(res)))
+    try:
+        info = FitInfo()
+        check_fit(L.bnr_fit_get_info(res, C.byref(info)))
+        rx, rg = np.empty(V), np.empty(q)
+        check_fit(L.bnr_fit_rhat(res, rx.ctypes.data_as(_DP), rg.ctypes.data_as(_DP)))
+        dev_summary = None
+        if info.summary_ok:
+            gm, gl, gh, xm = np.empty(q), np.empty(q), np.empty(q), np.empty(V)
+            check_fit(L.bnr_fit_summary(res, *(a.ctypes.data_as(_DP) for a in (gm, gl, gh, xm))))
+            dev_summary = dict(interval=interval, mean=gm, lower=gl, upper=gh, xi_mean=xm, V=V, q=q)
+        ess = None
+        if info.ess_ok:
+            ex, eg = np.empty(V), np.empty(q)
+            check_fit(L.bnr_fit_ess(res, ex.ctypes.data_as(_DP), eg.ctypes.data_as(_DP)))
+            ess = dict(xi=ex, gamma=eg, max_lag=ess_max_lag)
+        st = Table()
+        rows = int(info.rows)
+        shapes = {"tau2": (1, 1), "u": (R, V), "xi": (V, 1), "gamma": (q, 1), "S": (q, 1), "theta": (1, 1),
+                  "Delta": (1, 1), "M": (R, R), "mu": (1, 1), "lam": (R, 1), "pi": (R, 3)}
+        names = list(_UNI) if return_state == "full" else (["xi", "gamma"] if return_state == "gamma_xi" else [])
+        for k in names:
+            shp = shapes[k]
+            out = np.empty(rows * shp[0] * shp[1])
+            check_fit(L.bnr_fit_state(res, VAR[k], out.ctypes.data_as(_DP)))
+            st[k] = out.reshape((rows,) + shp, order="F")
+        status = []
+        for d in range(info.n_devices):
+            h = C.c_void_p()
+            check_fit(L.bnr_fit_handle(res, d, C.byref(h)))
+            s_ = np.zeros(num_chains, dtype=np.int32)
+            check(L.bnr_status(h, s_.ctypes.data_as(C.POINTER(C.c_int32))))
+            status.append(s_)
+        extra = dict(status=np.concatenate(status), tot_generated=int(info.tot_generated), seed=seed,
+                     gamma_mode={1: "nform", 2: "qform"}[int(info.gamma_mode)], device_summary=dev_summary,
+                     rhat_streamed=bool(info.streamed), n_psrf=int(info.n_psrf), total_chains=int(info.total_chains),
+                     n_devices=int(info.n_devices), exchange={0: "none", 1: "nccl", 2: "peer-copy"}[int(info.exchange)],
+                     ess=ess)
+        return Results(st, rx, rg, int(info.burn_in), int(info.sampled), extra)
+    finally:
+        L.bnr_fit_free(res)
 
 
 def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None, nburn=30000, nsamples=20000,
         mingen=0, maxgen=0, psrf_cutoff=1.01, x_transform=True, suppress_timer=False, num_chains=2, seed=None,
         purge_burn=None, filename="parameters.log", eta=None, zeta=None, iota=None, a_delta=None, b_delta=None,
-        nu=None, device=0, return_state="full", verbose=False, chain_offset=0):
+        nu=None, device=0, return_state="full", verbose=False, chain_offset=0, n_devices=1, ess_max_lag=0,
+        gamma_mode="auto", chain_groups=0):
     """Drop-in for `Fit!(X, y, R; ...)` (src/gibbs.jl:725-751).  Greek keyword names are accepted as in the
-    reference; ASCII aliases (eta, zeta, iota, a_delta, b_delta, nu) are equivalent.  Extra, engine-only
-    keywords: device, return_state ("full" | "gamma_xi" | "none": how much of chain 1's table is copied back),
-    chain_offset (global id of this GPU's first chain when several processes each fit a share of the chains;
-    default rank * num_chains inside a torch.distributed job, where num_chains is the count PER RANK and the R-hat
-    tables cover the chains of all ranks)."""
+    reference; ASCII aliases (eta, zeta, iota, a_delta, b_delta, nu) are equivalent.  Engine-only keywords: device,
+    n_devices (GPUs of this process to shard the chains over; num_chains is the count PER GPU), return_state
+    ("full" | "gamma_xi" | "none": how much of chain 1's table is copied back), ess_max_lag (> 0: gamma / xi ESS of the
+    retained draws in res.extra["ess"]), chain_offset (global id of the first chain), gamma_mode, chain_groups.
+    Inside a torch.distributed job every rank calls Fit with its own share of the chains; the R-hat tables then cover
+    the chains of all ranks."""
     def pick(greek, ascii_, default):
         return default if (greek is None and ascii_ is None) else (greek if greek is not None else ascii_)
 
@@ -243,11 +264,8 @@ def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None
     if seed is None:
         seed = random.randint(1, 55555)
     rank, world = _dist_world()
-    if world > 1:
-        if chain_offset == 0:
-            chain_offset = rank * num_chains
-        if rank != 0:
-            filename = None                  # one parameters.log per job
+    if world > 1 and rank != 0:
+        filename = None                  # one parameters.log per job
     if filename:
         with open(filename, "w") as fh:
             fh.write("BayesianNetworkRegression.jl Fit! function\n")
@@ -263,10 +281,11 @@ def Fit(X, y, R, *, η=None, V=30, ζ=None, ι=None, aΔ=None, bΔ=None, ν=None
     kw = dict(eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu,
               psrf_cutoff=psrf_cutoff, x_transform=x_transform, num_chains=num_chains, seed=seed,
               purge_burn=purge_burn, device=device, return_state=return_state, verbose=verbose,
-              chain_offset=chain_offset)
+              chain_offset=chain_offset, n_devices=n_devices, ess_max_lag=ess_max_lag, gamma_mode=gamma_mode,
+              chain_groups=chain_groups)
     if mingen > 0 and maxgen > 0:
         return generate_samples_dbl(X, y, R, mingen=mingen, maxgen=maxgen, **kw)
-    return generate_samples(X, y, R, nburn=nburn, nsamp=nsamples, maxburn=nburn + nsamples, **kw)
+    return generate_samples(X, y, R, nburn=nburn, nsamp=nsamples, **kw)
 
 
 def _prepare(X, y, R, nu, x_transform):
@@ -281,140 +300,31 @@ def _prepare(X, y, R, nu, x_transform):
     return Xn, y
 
 
-def _normalise_purge(purge_burn, nburn):
-    """src/gibbs.jl:930-936."""
-    if purge_burn is not None and purge_burn < nburn and purge_burn != 0:
-        if nburn % purge_burn != 0:
-            purge_burn = purge_burn - (nburn % purge_burn)
-        return purge_burn
-    return None
-
-
 def generate_samples(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_delta=1.0, nu=10, nburn=30000,
-                     nsamp=20000, maxburn=50000, psrf_cutoff=1.2, x_transform=True, num_chains=2, seed=None,
-                     purge_burn=None, device=0, return_state="full", verbose=False, engine_hook=None,
-                     chain_offset=0):
-    """The "traditional" scheme (generate_samples!, src/gibbs.jl:897-1020)."""
+                     nsamp=20000, psrf_cutoff=1.2, x_transform=True, num_chains=2, seed=None, purge_burn=None, **kw):
+    """The "traditional" scheme (generate_samples!, src/gibbs.jl:897-1020; maxburn = nburn + nsamp as Fit! passes it):
+    the control loop runs inside libbnr (bnr_fit)."""
     Xn, y = _prepare(X, y, R, nu, x_transform)
-    total = nburn + nsamp
-    purge_burn = _normalise_purge(purge_burn, nburn)
-    tot_save = total if purge_burn is None else nsamp + purge_burn
     seed = random.randint(1, 55555) if seed is None else seed
-    # R-hat needs the retained draws of EVERY chain.  Whenever those draws are always newly generated ones
-    # (nburn >= nsamp, and the purge ring leaves room) their split-half moments are streamed on the device and only
-    # chain 1 keeps a trace: memory is one chain's table instead of num_chains tables.
-    streamed = nburn >= nsamp and nsamp >= 1 and (purge_burn is None or nsamp + purge_burn <= nburn)
-    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, chain_offset=chain_offset,
-                 trace_rows=tot_save,
-                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=not streamed,
-                 trace_gamma_xi_chains=1, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
-    try:
-        eng.init_state()
-        if streamed:
-            _stream_last(eng, total - 1, nsamp)
-        _run_rows(eng, 2, nburn, total, purge_burn)
-        nb = purge_burn if purge_burn is not None else nburn
-        tot_generated = nburn + nsamp
-        rx, rg = _psrf(eng, nb, nsamp, streamed)
-        if verbose:
-            print("%d samples generated. Max PSRF XI: %.2f. Max PSRF Gamma: %.2f" % (tot_generated, _max(rx), _max(rg)))
-        while (_max(rx) > psrf_cutoff or _max(rg) > psrf_cutoff) and tot_generated < maxburn + nsamp:
-            if purge_burn is not None:
-                num2move = 1 if nsamp + purge_burn <= nburn else nsamp + purge_burn - nburn
-            else:
-                num2move = total - nburn
-            eng.copy_trace_rows(0, tot_save - num2move, num2move)
-            a_total = num2move + nburn if num2move > 1 else nburn
-            if streamed:
-                _stream_last(eng, a_total - num2move, nsamp)
-            _run_rows(eng, num2move + 1, (nburn - nsamp + num2move) if nburn > nsamp else 0, a_total, purge_burn)
-            tot_generated += a_total - num2move
-            rx, rg = _psrf(eng, nb, nsamp, streamed)
-            if verbose:
-                print("%d samples generated. Max PSRF XI: %.3f. Max PSRF Gamma: %.3f" %
-                      (tot_generated, _max(rx), _max(rg)))
-        if engine_hook is not None:
-            engine_hook(eng)
-        state = _fetch_state(eng, tot_save, return_state)
-        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
-                     device_summary=_device_summary(eng, nb, nsamp), rhat_streamed=streamed)
-        return Results(state, rx, rg, nb, nsamp, extra)
-    finally:
-        eng.close()
+    return _native_fit(Xn, y, R, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu, nburn=nburn,
+                       nsamp=nsamp, psrf_cutoff=psrf_cutoff, purge_burn=purge_burn, num_chains=num_chains, seed=seed, **kw)
 
 
 def generate_samples_dbl(X, y, R, *, eta=1.01, zeta=1.0, iota=1.0, a_delta=1.0, b_delta=1.0, nu=10, mingen=10000,
                          maxgen=100000, psrf_cutoff=1.01, x_transform=True, num_chains=2, seed=None,
-                         purge_burn=None, device=0, return_state="full", verbose=False, chain_offset=0):
-    """The "doubling generation" scheme (generate_samples_dbl!, src/gibbs.jl:1051-1198).
-
-    The retained window grows by mingen/2 draws per round, so its R-hat cannot come from one fixed streaming window.
-    When mingen is a multiple of 4 every window and every split half is a whole number of blocks of mingen/4 sweeps:
-    the device keeps per-block moments (bnr_set_moment_blocks) and merges them (bnr_moments_from_blocks), and only
-    chain 1 keeps a trace.  Otherwise all chains are traced and R-hat is taken from the trace rows."""
+                         purge_burn=None, **kw):
+    """The "doubling generation" scheme (generate_samples_dbl!, src/gibbs.jl:1051-1198), inside libbnr (bnr_fit)."""
     Xn, y = _prepare(X, y, R, nu, x_transform)
-    nburn = _jround(mingen / 2)
-    nsamp = mingen - nburn
-    total = nburn + nsamp
-    purge_burn = _normalise_purge(purge_burn, nburn)
-    tot_save = total if purge_burn is None else nsamp + purge_burn
-    halfburn = _jround(mingen / 2)
-    rounds = max(0, math.ceil((maxgen - total) / max(mingen, 1)))
-    capacity = max(tot_save, nsamp + (rounds + 1) * halfburn + halfburn)
     seed = random.randint(1, 55555) if seed is None else seed
-    blocked = mingen % 4 == 0 and mingen >= 8 and purge_burn is None
-    blk = mingen // 4
-    eng = Engine(Xn, y, R, num_chains=num_chains, seed=seed, device=device, chain_offset=chain_offset,
-                 trace_rows=capacity,
-                 trace_full_chains=1 if return_state == "full" else 0, trace_gamma_xi_all=not blocked,
-                 trace_gamma_xi_chains=1, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu)
-    try:
-        if blocked:
-            # block b = sweeps [b blk, (b+1) blk); after round k (k = 0: the first pass) mingen (k+1) sweeps exist and
-            # the last mingen (k+1) / 2 of them are retained: blocks [2(k+1), 4(k+1))
-            eng.set_moment_blocks(0, blk, 4 * (rounds + 1))
-        eng.init_state()
-        _run_rows(eng, 2, nburn, total, purge_burn)
-        nb = purge_burn if purge_burn is not None else nburn
-        tot_generated = total
-        tot_samples = nsamp
-        tot_sze = tot_save
-        k = 0
+    return _native_fit(Xn, y, R, eta=eta, zeta=zeta, iota=iota, a_delta=a_delta, b_delta=b_delta, nu=nu, mingen=mingen,
+                       maxgen=maxgen, psrf_cutoff=psrf_cutoff, purge_burn=purge_burn, num_chains=num_chains, seed=seed,
+                       **kw)
 
-        def psrf():
-            if blocked:
-                if (2 * (k + 1) * blk) // 2 < 2:
-                    return np.full(eng.V, np.nan), np.full(eng.q, np.nan)
-                eng.moments_from_blocks(2 * (k + 1), 2 * (k + 1))
-                return _psrf(eng, nb, nsamp, streamed=True)
-            return _psrf(eng, nb, nsamp)
 
-        rx, rg = psrf()
-
-        def unconverged():
-            mx, mg = _max(rx), _max(rg)
-            return mx > psrf_cutoff or mg > psrf_cutoff or np.isnan(mx) or np.isnan(mg)
-
-        while unconverged() and tot_generated < maxgen:
-            num2move = tot_samples
-            tot_samples += halfburn
-            nsamp = tot_samples
-            new_save = tot_samples + halfburn
-            eng.copy_trace_rows(0, tot_sze - num2move, num2move)
-            _run_rows(eng, num2move + 1, 0, new_save, purge_burn)
-            tot_sze = new_save
-            tot_generated += mingen
-            k += 1
-            rx, rg = psrf()
-            if verbose:
-                print("%d samples generated. Max PSRF XI: %.3f. Max PSRF Gamma: %.3f" %
-                      (tot_generated, _max(rx), _max(rg)))
-        state = _fetch_state(eng, tot_sze, return_state)
-        extra = dict(status=eng.status(), tot_generated=tot_generated, seed=seed, gamma_mode=eng.gamma_mode,
-                     device_summary=_device_summary(eng, nb, nsamp), rhat_streamed=blocked)
-        return Results(state, rx, rg, nb, nsamp, extra)
-    finally:
-        eng.close()
+def _summary_ranks(nsamp, interval):
+    """lw / hi of src/gibbs.jl:1221-1223 (Julia round = ties to even, 1-based indices)."""
+    lower = (100 - interval) / 200.0
+    return _jround(nsamp * lower), _jround(nsamp * (1.0 - lower))
 
 
 def Summary(results, interval=95, digits=3):

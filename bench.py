@@ -414,8 +414,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     res = bnr.Fit(X, y, R, nburn=nburn_e, nsamples=nsamp_e, num_chains=chains, seed=7, x_transform=False,
-                  filename=None, psrf_cutoff=float("inf"), device=local_rank, chain_offset=rank * chains,
-                  return_state="gamma_xi")
+                  filename=None, psrf_cutoff=float("inf"), device=local_rank, return_state="gamma_xi")
     summ = bnr.Summary(res) if nsamp_e >= 40 else None     # the reference's Summary needs >= 20 draws per tail index
     torch.cuda.synchronize(dev)
     e2e_s = max_over_ranks(time.perf_counter() - t0)

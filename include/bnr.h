@@ -235,6 +235,9 @@ int bnr_ess_from_stats_lags(int device, const double* dev_acov_parts, int32_t np
  * bnr_ess_stream_finish fills the same two statistics buffers as bnr_ess_accumulate: bnr_ess_device / bnr_export_ess /
  * bnr_ess_from_stats then work unchanged (nrows = ndraws).  max_lag is clamped like in bnr_ess_accumulate. */
 int bnr_ess_stream_begin(bnr_handle* h, int32_t max_lag, int64_t ndraws);
+/* the same with an explicit window: the sweeps first_sweep .. first_sweep + ndraws - 1 (1-based sweep numbers, none of
+ * them run yet) contribute */
+int bnr_ess_stream_window(bnr_handle* h, int32_t max_lag, int64_t first_sweep, int64_t ndraws);
 int bnr_ess_stream_finish(bnr_handle* h);
 
 /* chain groups (independent streams / CUDA graphs) the handle runs */
@@ -247,6 +250,82 @@ int bnr_launch_count(bnr_handle* h, int64_t* kernels);
  * X'a4+gamma+GIG, X gamma + scalar conditionals + record */
 int bnr_profile_sweep(bnr_handle* h, float* ms);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * bnr_fit: everything Fit!(X, y, R; ...) does between setup_X! and Results in one call -- chain generation with the
+ * purge_burn ring (run!, src/gibbs.jl:849-864), the PSRF-driven "extend burn-in" loop (generate_samples!, 897-1020) or
+ * the "doubling" loop (generate_samples_dbl!, 1051-1198; chosen when mingen > 0 && maxgen > 0 like Fit!, 744-750),
+ * R-hat over all chains (return_psrf_VOI, 771-789), the Summary statistics of chain 1 (1214-1250) and optionally the
+ * gamma / xi ESS.  A host wrapper only converts its arguments and wraps the returned buffers.
+ *
+ * Chains: base.num_chains chains PER DEVICE on n_devices GPUs of this process (devices base.device, base.device + 1,
+ * ...); global chain ids (RNG keys) are base.chain_offset + (ext_rank * n_devices + d) * num_chains + local id.  The only
+ * data that crosses NVLink are the split-half moments (32 (V + q) bytes per chain) and the ESS statistics, exchanged
+ * with ncclAllGather inside the library (libnccl.so.2 is loaded at run time; without it, peer copies).  Several
+ * PROCESSES can fit a share each (ext_world > 1): the library then calls `allgather` to exchange across processes.
+ * --------------------------------------------------------------------------------------------------------------- */
+#define BNR_STATE_NONE 0       /* no table of chain 1 is kept for bnr_fit_state */
+#define BNR_STATE_GAMMA_XI 1   /* gamma and xi rows of chain 1 */
+#define BNR_STATE_FULL 2       /* every state variable of chain 1 (what Results.state holds in the reference) */
+
+/* all-gather across the processes that call bnr_fit together: every process contributes `count` doubles at dev_send
+ * (device memory on `device`) and receives ext_world * count doubles, in rank order, at dev_recv.  Return 0 on success. */
+typedef int (*bnr_allgather_fn)(void* ctx, int device, const double* dev_send, double* dev_recv, int64_t count);
+
+typedef struct bnr_fit_params {
+  bnr_params base;          /* n, V, R, num_chains (per device), chain_offset, device, seed, hyper-parameters, gamma_mode,
+                               chain_groups; the trace_* fields are set by bnr_fit */
+  int64_t nburn, nsamples;  /* traditional scheme */
+  int64_t mingen, maxgen;   /* doubling scheme when both > 0 */
+  double psrf_cutoff;
+  int64_t purge_burn;       /* 0 = nothing */
+  int32_t return_state;     /* BNR_STATE_* */
+  int32_t n_devices;        /* GPUs of this process to shard the chains over (>= 1) */
+  int32_t interval;         /* credible level of the device Summary (95) */
+  int32_t ess_max_lag;      /* > 0: also the Geyer ESS of xi / gamma over the retained draws, lags 0..ess_max_lag */
+  int32_t verbose;          /* != 0: the reference's "samples generated. Max PSRF ..." lines on stderr */
+  int32_t ext_world, ext_rank;   /* multi-process use (0 / 1 = single process) */
+  bnr_allgather_fn allgather;
+  void* allgather_ctx;
+} bnr_fit_params;
+
+typedef struct bnr_fit_info {
+  int64_t tot_generated;    /* rows generated per chain (the reference's tot_generated) */
+  int64_t burn_in, sampled; /* Results.burn_in, Results.sampled: the retained draws are table rows burn_in .. burn_in + sampled - 1 (0-based) */
+  int64_t rows;             /* rows of chain 1's table (bnr_fit_state) */
+  int64_t n_psrf;           /* PSRF evaluations */
+  int32_t streamed;         /* R-hat came from streamed (or block) moments: no chain but the first kept a trace */
+  int32_t summary_ok, ess_ok;
+  int32_t gamma_mode, status_or, total_chains, n_devices;
+  int32_t exchange;         /* 0 none (one device), 1 NCCL, 2 peer copies */
+} bnr_fit_info;
+
+typedef struct bnr_fit_result bnr_fit_result;
+
+void bnr_fit_default_params(bnr_fit_params* p);
+const char* bnr_fit_last_error(void);
+/* X: n x q column-major (the matrix setup_X! builds), y: n.  The result owns its handles until bnr_fit_free. */
+int bnr_fit(const bnr_fit_params* p, const double* X, const double* y, bnr_fit_result** out);
+int bnr_fit_get_info(const bnr_fit_result* r, bnr_fit_info* info);
+int bnr_fit_rhat(const bnr_fit_result* r, double* rhat_xi, double* rhat_gamma);              /* [V], [q] */
+int bnr_fit_summary(const bnr_fit_result* r, double* gamma_mean, double* gamma_lo, double* gamma_hi, double* xi_mean);
+int bnr_fit_ess(const bnr_fit_result* r, double* ess_xi, double* ess_gamma);
+/* rows 0 .. info.rows - 1 of one state variable of chain 1 in the reference layout (iteration fastest) */
+int bnr_fit_state(bnr_fit_result* r, int32_t var, double* out);
+/* the engine handle of one of the result's devices (valid until bnr_fit_free), e.g. for bnr_status / bnr_get_trace */
+int bnr_fit_handle(bnr_fit_result* r, int32_t device_index, bnr_handle** h);
+int bnr_fit_free(bnr_fit_result* r);
+/* The control flow of bnr_fit as a pure host function (no GPU): the engine operations a fit would issue when its k-th
+ * PSRF evaluation returns psrf_max[k] as the maximum R-hat of both xi and gamma (NaN allowed; 0 beyond n_psrf).
+ * ops: [cap_ops][4] = (op, a, b, c) with op  0 create(trace rows, all chains traced, full-state chains)  1 init
+ *   2 run(a sweeps)  3 set trace row a  4 copy rows (dst a, src b, count c)  5 moment window(first sweep a, length b)
+ *   6 moment blocks(first a, block length b, count c)  7 PSRF from trace rows [a, a + b)  8 PSRF from the streamed
+ *   window  9 PSRF from blocks [a, a + b)  10 ESS window(first sweep a, length b).
+ * Used by the CPU test-suite to check the loops against the restated reference (oracle/psrf_loops.py). */
+int bnr_fit_plan(const bnr_fit_params* p, const double* psrf_max, int32_t n_psrf, int64_t* ops, int64_t cap_ops,
+                 int64_t* n_ops, bnr_fit_info* info);
+/* device-to-device copy helper for all-gather callbacks written in a host language without a CUDA binding */
+int bnr_device_copy(int device, void* dev_dst, const void* dev_src, int64_t bytes);
+
 /* ---- parity-test hooks (tests only) ---- */
 /* Injected basic variates replacing Philox: host array [num_chains][per_chain], layout documented in
  * oracle/bnr_oracle.py:draw_layout (sweep) / init_layout (init).  NULL switches injection off. */
@@ -258,6 +337,10 @@ int bnr_step(bnr_handle* h, int32_t cond);
 int bnr_finish_sweep(bnr_handle* h);
 int bnr_enable_aux(bnr_handle* h, int32_t on);
 int bnr_get_aux(bnr_handle* h, int32_t chain, int32_t aux_id, double* out, int64_t capacity);
+/* the Cholesky-with-jitter ladder of update_u_xi! (src/gibbs.jl:322-347) applied by the device routine the sweep uses
+ * to a caller-supplied R x R matrix (col-major): A_used = the matrix that finally factored (A, A + 1e-5 I or
+ * A + 5e-5 I), L = its lower factor, status = BNR_ST_JITTER / BNR_ST_SIGMA_NOTPD bits */
+int bnr_test_chol_jitter(bnr_handle* h, int32_t R, const double* A, double* A_used, double* L, int32_t* status);
 /* raw basic variates of the production RNG for a draw site (lets the oracle replay Philox mode):
  * kind 0 = uniform, 1 = normal; fills out[count] with the first `count` values of stream
  * (iteration, site, element) of local chain `chain`. */

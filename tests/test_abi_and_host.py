@@ -1,6 +1,6 @@
 """CPU-side checks: the C-ABI library loads and exports every symbol include/bnr.h declares (no compute calls
-without a GPU), the ctypes prototypes cover the header, and the host-side Fit!/Summary logic (row bookkeeping of
-run!, purge_burn normalisation, Summary tables) behaves like the reference."""
+without a GPU), the ctypes prototypes cover the header, and the host-side Fit!/Summary logic (Summary tables, input
+formats) behaves like the reference.  The control loops of bnr_fit are checked in tests/test_fit_plan.py."""
 import ctypes
 import os
 import re
@@ -60,67 +60,6 @@ def test_bad_arguments_rejected_before_any_cuda_call(bnr):
         bnr.Engine(np.zeros((4, 11)), np.zeros(4), 3)        # 11 is not V(V+1)/2
     with pytest.raises(ValueError):
         bnr.Fit(np.zeros((4, 10)), np.zeros(4), 12, ν=10, x_transform=False, filename=None)   # nu < R
-
-
-class FakeEngine:
-    """Records what the host logic asks of the engine (rows written, copies)."""
-
-    def __init__(self, rows):
-        self.table = [None] * rows
-        self.trace_row = 0
-        self.sweep = 0
-        self.table[0] = 0
-
-    def run(self, n):
-        for _ in range(n):
-            self.sweep += 1
-            if self.trace_row < len(self.table):
-                self.table[self.trace_row] = self.sweep
-            self.trace_row += 1
-
-    def copy_trace_rows(self, dst, src, count=1):
-        self.table[dst:dst + count] = self.table[src:src + count]
-
-
-def _reference_run(table, first_index, nburn, total, purge_burn, sweep):
-    """Literal run! (src/gibbs.jl:849-864), 1-based."""
-    j = first_index
-    for i in range(first_index, total + 1):
-        sweep += 1
-        table[j - 1] = sweep
-        if purge_burn is not None and i < nburn and j == purge_burn + 1:
-            table[0] = table[j - 1]
-            j = 1
-        j += 1
-    return sweep
-
-
-@pytest.mark.parametrize("nburn,nsamp,purge", [(40, 30, None), (40, 30, 10), (40, 30, 7), (100, 20, 25), (12, 50, 5)])
-def test_run_rows_matches_reference_loop(bnr, nburn, nsamp, purge):
-    from bnr_b200 import fit
-    pb = fit._normalise_purge(purge, nburn)
-    total = nburn + nsamp
-    rows = total if pb is None else nsamp + pb
-    eng = FakeEngine(rows)
-    eng.trace_row = 1
-    fit._run_rows(eng, 2, nburn, total, pb)
-    want = [None] * rows
-    want[0] = 0
-    _reference_run(want, 2, nburn, total, pb, 0)
-    assert eng.table == want
-    assert eng.sweep == total - 1
-    # the retained rows are the last nsamp sweeps
-    nb = pb if pb is not None else nburn
-    assert eng.table[nb:nb + nsamp] == list(range(total - nsamp, total))
-
-
-def test_purge_normalisation(bnr):
-    from bnr_b200 import fit
-    assert fit._normalise_purge(None, 100) is None
-    assert fit._normalise_purge(0, 100) is None
-    assert fit._normalise_purge(100, 100) is None          # not < nburn
-    assert fit._normalise_purge(10, 100) == 10
-    assert fit._normalise_purge(30, 100) == 30 - 100 % 30  # src/gibbs.jl:931-933
 
 
 def test_summary_matches_goldens(bnr, golden):
@@ -186,13 +125,13 @@ def test_input_formats_roundtrip(bnr, tmp_path, golden):
         bnr.read_matrix_networks(str(bad))
 
 
-def _build_c_client(tmp_path):
+def _build_c_client(tmp_path, name="abi_smoke"):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "bayesiannetworkregression.jl_b200")
-    exe = str(tmp_path / "abi_smoke")
+    exe = str(tmp_path / name)
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
-                    os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", pkg, "-lbnr",
+                    os.path.join(root, "tests", "c", name + ".c"), "-o", exe, "-L", pkg, "-lbnr",
                     "-Wl,-rpath," + pkg, "-lm"], check=True)
     return exe
 
@@ -208,6 +147,19 @@ def test_header_is_plain_c_and_links(bnr, tmp_path):
         assert r.returncode == 0, r.stdout + r.stderr
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+
+
+def test_c_fit_client_links_and_refuses_without_gpu(bnr, tmp_path):
+    """tests/c/fit_client.c drives a whole doubling-scheme Fit through bnr_fit from plain C (on the GPU: see
+    tests/test_gpu_engine.py); here: it compiles as strict C99 against the header and stops with BNR_ENODEV."""
+    import subprocess
+    import torch
+    exe = _build_c_client(tmp_path, "fit_client")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3, r.stdout + r.stderr
 
 
 def test_product_never_touches_the_oracle():

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 baseline of the round-1 kernels: per-config phases + launch lists, few-chain C3, honest CPU baseline
-cd "$(dirname "$0")/.."
-B="python scratch/bench_r1.py --no-cpu-baseline --steps 100 --warmup 6"
+cd "$(dirname "$0")/../.."
+B="python tools/gpu_runs/bench_r1.py --no-cpu-baseline --steps 100 --warmup 6"
 for c in c2 c4 c5; do
   $B --config $c > gpurun_out/r2base_$c.json 2> gpurun_out/r2base_$c.err
 done
@@ -24,7 +24,7 @@ for cfg, ch, sw in (("c3", 64, 10), ("c2", 16, 60)):
 print(json.dumps(out))
 PY
 for c in c4 c5; do
-  CMD="python scratch/bench_r1.py --no-cpu-baseline --steps 12 --warmup 3 --profile-sweeps 1 --chain-groups 1 --config $c"
+  CMD="python tools/gpu_runs/bench_r1.py --no-cpu-baseline --steps 12 --warmup 3 --profile-sweeps 1 --chain-groups 1 --config $c"
   $CMD > gpurun_out/r2base_plain_$c.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 300 --csv --log-file gpurun_out/r2base_launches_$c.csv $CMD > gpurun_out/r2base_ncu_$c.log 2>&1
 done

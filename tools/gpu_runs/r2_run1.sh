@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU check #1: parity tests, then the new bench line and few-chain variants
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2a_pytest.log
 timeout 600 python bench.py --steps 100 --warmup 6 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
 for g in 4 8; do

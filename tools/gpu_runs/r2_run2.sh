@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 B="python bench.py --no-cpu-baseline --no-other-configs --no-strong --ess-draws 0 --steps 100"
 run() { tag=$1; shift; timeout 200 "$@" > gpurun_out/r2b_$tag.json 2> gpurun_out/r2b_$tag.err; }
 for g in 1 2 4; do run c3x8_g$g $B --config c3 --chains 8 --chain-groups $g; done

@@ -1,0 +1,62 @@
+// lab harness (not part of the product): phase timings of k_potf2_inv from in-kernel globaltimer stamps, and
+// event timings of the panel-chain kernels on a synthetic SPD matrix.   nvcc ... -DBNR_POTF2_STAMPS tools/lab/potf2_lab.cu
+#include "../../bayesiannetworkregression.jl_b200/csrc/bnr_linalg.cu"
+#include <cstdio>
+#include <vector>
+namespace bnr { thread_local long long g_launches = 0; }
+using namespace bnr;
+
+int main(int argc, char** argv) {
+  const int C = argc > 1 ? atoi(argv[1]) : 8, N = argc > 2 ? atoi(argv[2]) : 1024;
+  const int T = N / PB;
+  const size_t cs = (size_t)N * N;
+  double *G, *G0, *Linv, *xout; int* status;
+  cudaMalloc(&xout, sizeof(double) * (size_t)C * N);
+  cudaMalloc(&G, sizeof(double) * cs * C + 16384); cudaMalloc(&G0, sizeof(double) * cs * C + 16384);
+  cudaMalloc(&Linv, sizeof(double) * (size_t)C * T * PB * PB); cudaMalloc(&status, sizeof(int) * C);
+  cudaMemset(status, 0, sizeof(int) * C);
+  std::vector<double> h(cs);
+  for (int j = 0; j < N; ++j)
+    for (int i = 0; i < N; ++i) h[(size_t)j * N + i] = (i == j) ? N + 1.0 : 0.5 + 0.3 * (((i * 31 + j * 17) % 13) / 13.0);
+  for (int c = 0; c < C; ++c) cudaMemcpy(G0 + c * cs, h.data(), sizeof(double) * cs, cudaMemcpyHostToDevice);
+  linalg_setup();
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto timeit = [&](const char* name, auto fn) {
+    float best = 1e9;
+    for (int r = 0; r < 6; ++r) {
+      cudaMemcpy(G, G0, sizeof(double) * cs * C, cudaMemcpyDeviceToDevice);
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0); fn(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("%-34s %8.1f us   (%s)\n", name, best * 1e3, cudaGetErrorString(cudaGetLastError()));
+  };
+  for (int J = 0; J < 2; ++J) {
+    char nm[64]; snprintf(nm, 64, "k_potf2_inv J=%d late=%d", J, J > 0);
+    timeit(nm, [&] { k_potf2_inv<<<C, 256, POTF2_SMEM>>>(G, cs, N, J, Linv, T, status, J > 0); });
+#ifdef BNR_POTF2_STAMPS
+    unsigned long long st[64];
+    cudaMemcpyFromSymbol(st, g_potf2_stamps, sizeof(st));
+    const char* names[18] = {"start", "load(+late update)", "s0 regchol", "s0 below", "s0 trailing", "s1 regchol", "s1 below",
+                             "s1 trailing", "s2 regchol", "s2 below", "s2 trailing", "s3 regchol", "s3 below", "s3 trailing",
+                             "factor store", "diag inverses", "4 DMMA stages", "copy + Linv store"};
+    for (int i = 1; i < 18; ++i) printf("    %-22s %7.2f us\n", names[i], (st[i] - st[i - 1]) * 1e-3);
+    printf("    total                  %7.2f us\n", (st[17] - st[0]) * 1e-3);
+#endif
+  }
+  for (int ns = 1; ns <= 4; ns *= 2) {
+    char nm[96];
+    snprintf(nm, 96, "k_trsm_dmma 1 tile/chain, %d strips", ns);
+    timeit(nm, [&] { dim3 g(C, ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, N, 0, 1, Linv, (size_t)T * PB * PB, ns); });
+    snprintf(nm, 96, "k_trsm_dmma T-2 tiles/chain, %d strips", ns);
+    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, N, 0, 2, Linv, (size_t)T * PB * PB, ns); });
+    snprintf(nm, 96, "k_chol_update depth 128, T-2 tiles, %d strips", ns);
+    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, G, N, N, 8, 1, 2, ns); });
+    const int jb = 4 < T ? 4 : T - 1;
+    snprintf(nm, 96, "k_chol_update depth 512, col %d incl diag, %d strips", jb, ns);
+    timeit(nm, [&] { dim3 g(C, (T - jb) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, G, N, N, 32, jb, jb, ns); });
+  }
+  timeit("k_bwd_stream", [&] { k_bwd_stream<<<C, 256, bwd_smem(N)>>>(G, cs, N, N - 1, Linv, xout, N, nullptr, 0, bwd_stages(N)); });
+  timeit("empty launch pair", [&] { k_augment<<<1, 256>>>(G, cs, N, 1, G0, N, nullptr, nullptr); });
+  return 0;
+}
