@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/bnr.h"
 #include "bnr_engine.cuh"
 #include "bnr_kernels.h"
@@ -31,6 +32,12 @@ static double wall_ms() {
 }
 namespace bnr { thread_local long long g_launches = 0; }
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+// NVTX range over a scope: one per conditional of the sweep where the kernels are enqueued (eager
+// sweeps, bnr_step, graph capture) and one per bnr_run; free when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t _e = (call);                                                                             \
@@ -233,9 +240,9 @@ extern "C" int bnr_create(const bnr_params* p, const double* X, const double* y,
     return fail(BNR_ENODEV, "no CUDA device visible: libbnr has no CPU fallback");
   if (p->device < 0 || p->device >= ndev) return fail(BNR_EINVAL, "device ordinal out of range");
   CK(cudaSetDevice(p->device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, p->device));
-  if (prop.major < 10) return fail(BNR_ENODEV, "libbnr is built for sm_100a (B200) only");
+  int cc_major = 0;      // (cudaGetDeviceProperties takes anything from 1 to 120 ms; one attribute is all that is needed)
+  CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device));
+  if (cc_major < 10) return fail(BNR_ENODEV, "libbnr is built for sm_100a (B200) only");
 
   bnr_handle* h = new bnr_handle();
   h->p = *p;
@@ -385,7 +392,12 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     // chain groups (see ChainGroup): 2 by default once there are enough chains to split
     // default: 2 groups once the SYRK of half the chains fills the GPU for several waves; 4 when the chains are few
     // (then the per-group latency chain, not the tensor pipe, bounds the sweep and more of them must overlap)
-    int ng = p->chain_groups > 0 ? p->chain_groups : (d.C >= 96 ? 2 : (d.C >= 48 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1))));
+    // measured on B200: 64 chains of config 3: 2 / 3 / 4 groups -> 11.07 / 10.91 / 11.10 ms per sweep; 8 chains: 2 / 4 / 8
+    // -> 2.02 / 1.95 / 2.16 ms; config 4 (8 chains, split-K SYRK: every group's SYRK fills the GPU by itself): 2 / 4 ->
+    // 1.69 / 1.84 ms
+    int ng_auto = d.C >= 96 ? 2 : (d.C >= 48 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
+    if (d.gmode == BNR_GAMMA_NFORM && d.C < 48 && d.C >= 4 && syrk_splits(d, d.C) > 1) ng_auto = 2;
+    int ng = p->chain_groups > 0 ? p->chain_groups : ng_auto;
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > d.C) ng = d.C;
     h->n_groups = ng;
@@ -541,20 +553,26 @@ static void run_gamma(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s,
 // stream, so that they -- of this chain group and of the others -- get an SM as soon as any SYRK CTA retires instead
 // of queueing behind the SYRK's remaining CTAs.
 static void enqueue_sweep(Engine& e, double* ws, const ForkJoin& fj, cudaStream_t s) {
+  NvtxRange sweep("bnr sweep");
   const bool fork_syrk = fj.side != nullptr && e.d.gmode == BNR_GAMMA_NFORM && !e.aux.G_copy;
   if (fork_syrk) {
+    NvtxRange r("gamma: G = X D X' + I (forked)");
     cudaEventRecord(fj.fork, s);
     cudaStreamWaitEvent(fj.side, fj.fork, 0);
     launch_syrk_G(e, fj.side);
     cudaEventRecord(fj.join, fj.side);
   }
-  launch_tau2(e, s);
-  launch_uxi(e, s);
+  { NvtxRange r("tau2"); launch_tau2(e, s); }
+  { NvtxRange r("u, xi"); launch_uxi(e, s); }
   std::swap(e.u, e.u_alt);          // u now holds the new draw (pointer swap is baked per captured sweep)
-  run_gamma(e, ws, fj, s, 3, fork_syrk);
-  launch_x_times(e, 0, e.gamma, e.xg, ws, s);
-  launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
-                       (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
+  { NvtxRange r("gamma + D (GIG)"); run_gamma(e, ws, fj, s, 3, fork_syrk); }
+  {
+    NvtxRange r("theta, Delta, M, mu, Lambda, pi");
+    launch_x_times(e, 0, e.gamma, e.xg, ws, s);
+    launch_finish(e, (1 << BNR_COND_THETA) | (1 << BNR_COND_DELTA) | (1 << BNR_COND_M) | (1 << BNR_COND_MU) |
+                         (1 << BNR_COND_LAMBDA) | (1 << BNR_COND_PI), s);
+  }
+  NvtxRange r("record");
   launch_record(e, 1, s);
   if (e.ess_ring) launch_ess_stream(e, s);
   launch_advance(e, 1, s);
@@ -643,6 +661,7 @@ extern "C" int bnr_init_state(bnr_handle* h) {
 
 extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
   if (!h || n_iters < 0) return fail(BNR_EINVAL, "bad arguments");
+  NvtxRange range("bnr_run");
   CK(cudaSetDevice(h->p.device));
   CK(cudaEventRecord(h->ev0, h->stream));
   if (!h->xg_valid) { const long long b0 = g_launches; refresh_xg(h); h->launches += g_launches - b0; }
@@ -731,6 +750,7 @@ extern "C" int bnr_copy_trace_rows(bnr_handle* h, int64_t dst, int64_t src, int6
   if (!h || dst < 0 || src < 0 || count < 0) return fail(BNR_EINVAL, "bad arguments");
   CK(cudaSetDevice(h->p.device));
   Engine& e = h->e;
+  if (e.trace_rows == 0 || (!e.tr_full && !e.tr_gx)) return BNR_OK;     // this handle records no traces: nothing to move
   if (dst + count > e.trace_rows || src + count > e.trace_rows) return fail(BNR_EINVAL, "rows out of range");
   if (count == 0 || dst == src) return BNR_OK;
   // rows are contiguous per chain; regions may overlap -> stage through one temporary (stream order keeps the chains apart)

@@ -1317,7 +1317,7 @@ void launch_build_P(const Engine& e, cudaStream_t s) {
 //       k_potf2_inv    factor + invert the diagonal block                                                  [main]
 //       k_trsm_dmma    tiles (i, J), i > J                                                                 [main]
 //
-// (B) latency schedule -- few chains (chains x (T-1) <= 64), the GPU is mostly idle and the length of the dependent
+// (B) latency schedule -- few chains (chains x (T-1) <= 128; measured crossover between 16 and 32 chains at T = 8), the GPU is mostly idle and the length of the dependent
 //     chain is what counts.  Left-looking with a one-panel look-ahead; per panel J, in program order (every tile sees its
 //     updates in this order on any schedule):
 //       PA(J)      k_potf2_inv    D_JJ -= L[J,J-1] L[J,J-1]' (late part, in the kernel), factor, invert       [main]
@@ -1341,7 +1341,7 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
   const size_t ls = (size_t)T * PB * PB;
   static const bool serial = getenv("BNR_CHOL_SERIAL") != nullptr;        // debugging knob: program order on one stream
   static const int forced = getenv("BNR_CHOL_SCHEDULE") ? atoi(getenv("BNR_CHOL_SCHEDULE")) : 0;   // 1 = (A), 2 = (B)
-  const bool latency = forced ? forced == 2 : (long long)d.C_total * (T - 1) <= 64;
+  const bool latency = forced ? forced == 2 : (long long)d.C_total * (T - 1) <= 128;
   ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
 
   if (!latency) {

@@ -595,6 +595,21 @@ def test_plain_c_client_runs_a_fit(bnr, tmp_path):
     assert "sweeps 80" in r.stdout
 
 
+def test_plain_c_client_runs_bnr_fit(bnr, tmp_path):
+    """tests/c/fit_client.c: a whole doubling-scheme Fit through bnr_fit from plain C; with two GPUs also the chains
+    sharded over both inside the library (moments all-gathered with NCCL) against one GPU holding all chains."""
+    import subprocess
+    import torch
+    from test_abi_and_host import _build_c_client
+    exe = _build_c_client(tmp_path, "fit_client")
+    ndev = 2 if torch.cuda.device_count() >= 2 else 1
+    r = subprocess.run([exe, str(ndev)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "tot_generated 120 burn_in 20 sampled 60 rows 80" in r.stdout
+    if ndev == 2:
+        assert "two devices: 4 chains" in r.stdout
+
+
 def test_block_moments_equal_trace_moments(bnr):
     """Per-block streaming moments merged over a window (what the doubling scheme uses instead of all-chain traces)
     give the same split R-hat as the two-pass reduction of the recorded rows, for every window made of whole blocks."""

@@ -122,3 +122,10 @@ def test_fit_over_two_devices_equals_one_device(bnr, exchange, monkeypatch):
     np.testing.assert_array_equal(two.state["gamma"], one.state["gamma"])
     np.testing.assert_allclose(two.extra["ess"]["gamma"], one.extra["ess"]["gamma"], rtol=1e-9)
     assert len(two.extra["status"]) == 6
+    # the doubling scheme with block moments (only chain 1 keeps a trace: the second device records nothing)
+    kd = dict(mingen=40, maxgen=120, seed=17, x_transform=False, filename=None, psrf_cutoff=0.0, return_state="gamma_xi")
+    two = bnr.Fit(X, y, 3, num_chains=3, n_devices=2, **kd)
+    one = bnr.Fit(X, y, 3, num_chains=6, n_devices=1, **kd)
+    assert two.extra["tot_generated"] == one.extra["tot_generated"] == 120 and two.extra["rhat_streamed"]
+    np.testing.assert_allclose(two.rhatγ.γ, one.rhatγ.γ, rtol=1e-12)
+    np.testing.assert_array_equal(two.state["gamma"], one.state["gamma"])
