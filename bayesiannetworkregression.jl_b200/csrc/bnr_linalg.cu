@@ -18,6 +18,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// -x by flipping the sign bit (an integer op: the FP64 pipe is what the DMMA loop is bound by)
+__device__ __forceinline__ double neg_bits(double x) {
+  return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ull);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -112,6 +116,10 @@ __device__ __forceinline__ void syrk_diag_frags(const double* sj, const double* 
     const double sk = ss[kr];
     a2[0] = row[W * 8] * sk;
     a2[1] = row[(15 - W) * 8] * sk;
+  } else if (MODE == 1) {
+    // C -= A A': the accumulators start from C (syrk_diag_tile) and the column operand enters negated
+    a2[0] = neg_bits(row[W * 8]);
+    a2[1] = neg_bits(row[(15 - W) * 8]);
   } else {
     a2[0] = row[W * 8];
     a2[1] = row[(15 - W) * 8];
@@ -126,8 +134,21 @@ __device__ __forceinline__ void syrk_diag_tile(const double* smem, unsigned long
                                                double* __restrict__ Cc, int np, int i0, double diag_add) {
   constexpr int NA = 16 - W;        // fragments of column W
   double acc[17][2];
+  if (MODE == 1) {
+    // MODE 1 updates C in place.  Its 17 fragments are loaded NOW, as independent 16-byte loads that overlap the
+    // pipeline fill: the old load-subtract-store epilogue serialised them (a later load may alias an earlier store),
+    // which cost ~25 us per CTA once G (512 MB) lives in HBM -- half of all stall samples of k_chol_update.
 #pragma unroll
-  for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int t = 0; t < 17; ++t) {
+      const int jf = (t < NA) ? W : 15 - W;
+      const int ifr = (t < NA) ? W + t : t - 1;
+      const double2 v = *reinterpret_cast<const double2*>(Cc + (size_t)(i0 + jf * 8 + lr) * np + i0 + ifr * 8 + 2 * lk);
+      acc[t][0] = v.x; acc[t][1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 17; ++t) acc[t][0] = acc[t][1] = 0.0;
+  }
   double a2[2][2], bfr[2][NA];
   mbar_wait(&full[0], 0);
   const double* sj = smem;
@@ -164,9 +185,8 @@ __device__ __forceinline__ void syrk_diag_tile(const double* smem, unsigned long
       v.x = acc[t][0] + (i == j ? diag_add : 0.0);
       v.y = acc[t][1] + (i + 1 == j ? diag_add : 0.0);
     } else {
-      v = *p;
-      v.x -= acc[t][0];
-      v.y -= acc[t][1];
+      v.x = acc[t][0];               // MODE 1: C - A A' accumulated in place
+      v.y = acc[t][1];
     }
     *p = v;
   }
@@ -188,6 +208,9 @@ __device__ __forceinline__ void syrk_strip_frags(const double* sj, const double*
     const double sk = ss[kr];
     af[0] = rj[f0 * 8] * sk;
     af[1] = rj[f1 * 8] * sk;
+  } else if (MODE == 1) {
+    af[0] = neg_bits(rj[f0 * 8]);    // C -= A_i A_j': accumulators start from C, the 2-fragment operand enters negated
+    af[1] = neg_bits(rj[f1 * 8]);
   } else {
     af[0] = rj[f0 * 8];
     af[1] = rj[f1 * 8];
@@ -204,11 +227,24 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
                                                 unsigned long long* empty, int nk, int warp, int lk, int lr, int lane,
                                                 double* __restrict__ Cc, int np, int i0, int j0) {
   double acc[2][NF][2];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < NF; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int f0 = (MODE == 2) ? warp : 2 * warp, f1 = (MODE == 2) ? 15 - warp : 2 * warp + 1;
+  if (MODE == 1) {
+    // in-place update: the tile's current values are the initial accumulators (see syrk_diag_tile)
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) {
+        const double2 v = *reinterpret_cast<const double2*>(Cc + (size_t)j * np + i0 + nf * 8 + 2 * lk);
+        acc[mf][nf][0] = v.x; acc[mf][nf][1] = v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < NF; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  }
   const int lim0 = 2 * f0 + 2, lim1 = 2 * f1 + 2;       // MODE 2: k4-steps that can still reach the fragment
   double af[2][2], bf[2][NF];
   mbar_wait(&full[0], 0);
@@ -255,14 +291,8 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
       const int i = i0 + nf * 8 + 2 * lk;
       double2* p = reinterpret_cast<double2*>(Cc + (size_t)j * np + i);
       double2 v;
-      if (MODE != 1) {
-        v.x = acc[mf][nf][0];
-        v.y = acc[mf][nf][1];
-      } else {
-        v = *p;
-        v.x -= acc[mf][nf][0];
-        v.y -= acc[mf][nf][1];
-      }
+      v.x = acc[mf][nf][0];          // MODE 1: C - A_i A_j' accumulated in place
+      v.y = acc[mf][nf][1];
       *p = v;
     }
   }
