@@ -291,7 +291,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   // dynamic shared memory of the per-chain kernels grows with V*R
   const size_t need = sizeof(double) * ((size_t)d.V * d.R + 2 * d.R * d.R + 2 + 4 * (2 * d.V + 2 * d.R * d.R + 3 * d.R));
   if (need > 200 * 1024 || d.gdim > chol_max_dim()) {
-    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R, or factored dimension > 4096)");
+    return fail(BNR_EINVAL, "problem too large for the per-chain shared-memory kernels (V*R > 200 KB of shared memory, or factored dimension > 8192)");
   }
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&h->ev0));
@@ -392,11 +392,11 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     // chain groups (see ChainGroup): 2 by default once there are enough chains to split
     // default: 2 groups once the SYRK of half the chains fills the GPU for several waves; 4 when the chains are few
     // (then the per-group latency chain, not the tensor pipe, bounds the sweep and more of them must overlap)
-    // measured on B200: 64 chains of config 3: 2 / 3 / 4 groups -> 11.07 / 10.91 / 11.10 ms per sweep; 8 chains: 2 / 4 / 8
-    // -> 2.02 / 1.95 / 2.16 ms; config 4 (8 chains, split-K SYRK: every group's SYRK fills the GPU by itself): 2 / 4 ->
-    // 1.69 / 1.84 ms
-    int ng_auto = d.C >= 96 ? 2 : (d.C >= 48 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
-    if (d.gmode == BNR_GAMMA_NFORM && d.C < 48 && d.C >= 4 && syrk_splits(d, d.C) > 1) ng_auto = 2;
+    // measured on B200 (round 2, 100-sweep runs): 64 chains of config 3 with 2 / 3 / 4 / 6 / 8 groups -> 10.94 / 10.97 /
+    // 11.02 / 11.17 / 11.29 ms per sweep; 32 chains: 2 / 3 / 4 -> 5.87 / 5.86 / 5.96 ms; 8 chains: 2 / 4 / 8 -> 2.02 /
+    // 1.95 / 2.16 ms; config 4 (8 chains, split-K SYRK: every group's SYRK fills the GPU by itself): 2 / 4 -> 1.69 / 1.84
+    int ng_auto = d.C >= 24 ? 2 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1));
+    if (d.gmode == BNR_GAMMA_NFORM && d.C >= 4 && syrk_splits(d, d.C) > 1) ng_auto = 2;
     int ng = p->chain_groups > 0 ? p->chain_groups : ng_auto;
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > d.C) ng = d.C;

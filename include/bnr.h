@@ -136,6 +136,10 @@ typedef struct bnr_params {
 #define BNR_GAMMA_QFORM 2
 
 #define BNR_MAX_R 16
+/* Size limits (bnr_create returns BNR_EINVAL beyond them; the reference has none): R <= 16; the factored dimension --
+ * n + 1 for the n x n form, q + 1 for the q x q form, rounded up to a multiple of 128 -- at most 8192 (the back solve
+ * keeps the solution vector in shared memory); V * R doubles + a few R x R blocks must fit 200 KB of shared memory. */
+#define BNR_MAX_FACTOR_DIM 8192
 
 int bnr_version(void);
 const char* bnr_last_error(void);

@@ -645,10 +645,12 @@ def test_block_moments_equal_trace_moments(bnr):
     np.testing.assert_array_equal(a.state["γ"][-1, :, 0], last)
 
 
-@pytest.mark.parametrize("V,n,R,mode", [(40, 3000, 4, "nform"), (60, 2000, 5, "qform"), (300, 300, 9, "nform")])
+@pytest.mark.parametrize("V,n,R,mode", [(40, 3000, 4, "nform"), (60, 2000, 5, "qform"), (300, 300, 9, "nform"),
+                                        # beyond the 4096 limit of round 1: 34 panels (n-form), 40 panels (q-form)
+                                        (12, 4250, 3, "nform"), (100, 150, 3, "qform")])
 def test_unusual_shapes_factorisation_properties(bnr, V, n, R, mode):
-    """Tall n-form (24 panels of 128), long q-form (15 panels) and a large network (q = 45150): the factored matrix
-    satisfies L L' = G (resp. P) and G a4 = rhs-type residuals stay at rounding level; chains stay healthy."""
+    """Tall n-form (24 and 34 panels of 128), long q-form (15 and 40 panels) and a large network (q = 45150): the
+    factored matrix satisfies L L' = G (resp. P) and G a4 = rhs-type residuals stay at rounding level; chains stay healthy."""
     rng = np.random.default_rng(V + n)
     q = V * (V + 1) // 2
     X = rng.normal(size=(n, q)) * (rng.random((n, q)) < 0.4)
