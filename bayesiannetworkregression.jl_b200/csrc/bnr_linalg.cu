@@ -959,6 +959,106 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Depth-128 tile kernels of the latency schedule, operands resident in shared memory.
+//   MODE 2  panel solve     C[strip] = G[strip, J] Linv_J'                  (T1 / T2 of launch_cholesky)
+//   MODE 1  late update     C[strip] -= L[strip, J] L[J+1, J]'              (Ulate)
+// One CTA per (chain, row strip of 32 or 64 rows).  The ring-fed kernels above spend ~8 us per tile on their eight
+// pipeline stages (32 one-kilobyte TMA requests each, ~30 ns per request) around 2-4 us of DMMA work; here the two
+// operands arrive as 16-byte cp.async copies of all 256 threads (1.5-2 us for 160-200 KB), one barrier, then the same
+// fragments in the same k order as syrk_strip_tile (bit-identical results), and a direct store.
+// grid = (C, tiles * nstrip), block = 256.
+// ------------------------------------------------------------------------------------------------------------
+constexpr size_t small_tile_smem(int rows_i) { return sizeof(double) * ((size_t)PB * SY_LDS + (size_t)PB * (rows_i + 4)); }
+
+template <int MODE, int NF>
+__global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size_t chain_stride, int N, int jb, int ib_first,
+                                                    int nstrip, const double* __restrict__ Bj, size_t bj_chain_stride,
+                                                    int ldj, int kcol0) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int ROWS = NF * 8, LDI = ROWS + 4;       // LDI == 4 mod 16: conflict-free fragment loads
+  double* sJ = sm;                                   // [128 k][132]  j operand: sJ[k * SY_LDS + row]
+  double* sI = sm + PB * SY_LDS;                     // [128 k][LDI]  i operand (this CTA's row strip)
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lk = lane & 3, lr = lane >> 2;
+  const int ib = ib_first + (int)blockIdx.y / nstrip, strip = (int)blockIdx.y % nstrip;
+  const int i0 = ib * PB + strip * ROWS;
+  double* Gc = G + (size_t)c * chain_stride;
+  // sources (k-major: element (row, k) at base[row + ld * k]); kcol0 = first column of the contributing panel
+  const double* srcJ = Bj + (size_t)c * bj_chain_stride;
+  const double* srcI = Gc + (size_t)kcol0 * N + i0;
+  {
+    const int chunk = tid & 63, r0 = tid >> 6;       // j operand: 128 k-rows of 64 16-byte chunks
+#pragma unroll 8
+    for (int i = 0; i < PB / 4; ++i) {
+      const int k = r0 + 4 * i;
+      cp_async16(sJ + k * SY_LDS + chunk * 2, srcJ + (size_t)k * ldj + chunk * 2);
+    }
+    constexpr int CPR = ROWS / 2;                    // 16-byte chunks per k-row of the i operand
+    for (int id = tid; id < PB * CPR; id += 256) {
+      const int k = id / CPR, ch = id % CPR;
+      cp_async16(sI + k * LDI + ch * 2, srcI + (size_t)k * N + ch * 2);
+    }
+    cp_async_commit();
+  }
+  const int f0 = (MODE == 2) ? warp : 2 * warp, f1 = (MODE == 2) ? 15 - warp : 2 * warp + 1;
+  const int lim0 = 2 * f0 + 2, lim1 = 2 * f1 + 2;    // MODE 2: k4-steps that can still reach the column fragment
+  const int j0 = jb * PB;
+  double acc[2][NF][2];
+  if (MODE == 1) {                                   // in place: start from the tile's current values
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) {
+        const double2 v = *reinterpret_cast<const double2*>(Gc + (size_t)j * N + i0 + nf * 8 + 2 * lk);
+        acc[mf][nf][0] = v.x; acc[mf][nf][1] = v.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll 4
+  for (int k4 = 0; k4 < PB / 4; ++k4) {
+    const int kr = k4 * 4 + lk;
+    const double* rj = sJ + kr * SY_LDS + lr;
+    const double* ri = sI + kr * LDI + lr;
+    double af0 = rj[f0 * 8], af1 = rj[f1 * 8];
+    if (MODE == 1) { af0 = neg_bits(af0); af1 = neg_bits(af1); }
+    double bf[NF];
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) bf[nf] = ri[nf * 8];
+    if (MODE == 2) {
+      if (k4 < lim0) {
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) dmma884(acc[0][nf][0], acc[0][nf][1], af0, bf[nf]);
+      }
+      if (k4 < lim1) {
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) dmma884(acc[1][nf][0], acc[1][nf][1], af1, bf[nf]);
+      }
+    } else {
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) {
+        dmma884(acc[0][nf][0], acc[0][nf][1], af0, bf[nf]);
+        dmma884(acc[1][nf][0], acc[1][nf][1], af1, bf[nf]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf) {
+    const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf)
+      *reinterpret_cast<double2*>(Gc + (size_t)j * N + i0 + nf * 8 + 2 * lk) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward solve  L' x = b,  b = w (+ addz), w = row m of the factor (see above).  One CTA per chain streams the factor
 // once, bottom-right to top-left, in parts of BW_COLS columns x 128 rows through a multi-stage cp.async ring: every
 // thread issues 16-byte LDGSTS copies (a 1 KB column is one coalesced request of 64 threads).  The first version fed
@@ -1245,6 +1345,10 @@ void linalg_setup() {
   cudaFuncSetAttribute(k_trsm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SYRK_SMEM);
   cudaFuncSetAttribute(k_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM);
   cudaFuncSetAttribute(k_bwd_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_small_tile<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(32));
+  cudaFuncSetAttribute(k_small_tile<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(32));
+  cudaFuncSetAttribute(k_small_tile<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(64));
+  cudaFuncSetAttribute(k_small_tile<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(64));
 }
 
 // k-splits of the SYRK for a handle of C chains: when chains x tiles is below ~4 waves of CTAs, a CTA (one 128 x 128
@@ -1418,6 +1522,20 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
     const int ctas = d.C_total * tiles;
     return ctas * 4 <= 148 ? 4 : (ctas * 2 <= 148 ? 2 : 1);
   };
+  // panel solve of `rows` row blocks from ib_first of block column J: the shared-memory-resident kernel when the tiles
+  // are cut into strips (few chains), else the ring-fed one
+  static const bool small_tiles = getenv("BNR_NO_SMALL_TILES") == nullptr;
+  auto launch_trsm = [&](int J, int ib_first, int rows, int ns, cudaStream_t st) {
+    dim3 g(d.C, rows * ns);
+    const double* Lj = e.Linv + (size_t)J * PB * PB;
+    ++g_launches;
+    if (small_tiles && ns == 4)
+      k_small_tile<2, 4><<<g, 256, small_tile_smem(32), st>>>(e.G, cs, N, J, ib_first, 4, Lj, ls, PB, J * PB);
+    else if (small_tiles && ns == 2)
+      k_small_tile<2, 8><<<g, 256, small_tile_smem(64), st>>>(e.G, cs, N, J, ib_first, 2, Lj, ls, PB, J * PB);
+    else
+      k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM, st>>>(e.G, cs, N, m + 1, J, ib_first, Lj, ls, ns);
+  };
   for (int J = 0; J < T; ++J) {
     const bool has_side = J + 2 < T;
     if (fork && J >= 2) cudaStreamWaitEvent(s, evE[J - 2], 0);
@@ -1426,8 +1544,7 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
     if (J + 1 < T) {
       if (fork && J >= 1 && J + 1 < T) cudaStreamWaitEvent(s, evL[J - 1], 0);
       const int ns1 = strips(1);
-      dim3 g1(d.C, ns1);
-      ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls, ns1);
+      launch_trsm(J, J + 1, 1, ns1, s);
       if (fork && has_side) cudaEventRecord(evT[J], s);
     }
     if (has_side) {
@@ -1435,10 +1552,15 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
       if (fork) cudaStreamWaitEvent(side, evP[J], 0);
       const int ns2 = strips(rows);
       dim3 g2(d.C, rows * ns2);
-      ++g_launches; k_trsm_dmma<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, m + 1, J, J + 2, e.Linv + (size_t)J * PB * PB, ls, ns2);
+      launch_trsm(J, J + 2, rows, ns2, side);
       if (fork) cudaStreamWaitEvent(side, evT[J], 0);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1,
-                                                                   PB / SY_BK, J + 1, J + 2, ns2);
+      ++g_launches;
+      if (small_tiles && ns2 == 4)
+        k_small_tile<1, 4><<<g2, 256, small_tile_smem(32), side>>>(e.G, cs, N, J + 1, J + 2, 4, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB);
+      else if (small_tiles && ns2 == 2)
+        k_small_tile<1, 8><<<g2, 256, small_tile_smem(64), side>>>(e.G, cs, N, J + 1, J + 2, 2, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB);
+      else
+        k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1, PB / SY_BK, J + 1, J + 2, ns2);
       if (fork) cudaEventRecord(evL[J], side);
       ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, e.G, N, m + 1, (J + 1) * PB / SY_BK,
                                                                    J + 2, J + 2, ns2);
