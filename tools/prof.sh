@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 TAG=$1
 BASE="python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-other-configs --no-strong --ess-draws 0 --profile-sweeps 1 --chain-groups 1"
-for spec in "c3:--config c3" "c3x8:--config c3 --chains 8" "c2:--config c2"; do
+for spec in "c3:--config c3" "c3x8:--config c3 --chains 8" "c2:--config c2" "c4:--config c4" "c5:--config c5"; do
   name=${spec%%:*}; extra=${spec#*:}
   CMD="$BASE $extra"
   $CMD > gpurun_out/plain_${name}_$TAG.log 2>&1 &&
@@ -16,7 +16,7 @@ for K in k_gram_syrk k_potf2_inv k_chol_update k_trsm_dmma k_bwd_stream k_gamma_
   ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 1 -f -o gpurun_out/prof_${K}_$TAG $CMD > gpurun_out/ncu2_${K}_$TAG.log 2>&1
 done
 CMD="$BASE --config c3 --chains 8"
-for K in k_potf2_inv k_trsm_dmma; do
+for K in k_potf2_inv k_small_tile; do
   $CMD > gpurun_out/plain3_$TAG.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 1 -f -o gpurun_out/prof_x8_${K}_$TAG $CMD > gpurun_out/ncu3_${K}_$TAG.log 2>&1
 done
