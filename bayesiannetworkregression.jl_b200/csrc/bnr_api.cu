@@ -330,6 +330,8 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   DA(e.xg, C * d.np); DA(e.xv, C * d.np); DA(e.rhs, C * d.np);
   DA(e.G, C * d.gdim * d.gdim + 2048);
   DA(e.Linv, C * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N);
+  // the blocks above the diagonal of every inverted panel are exact zeros that k_potf2_inv never writes
+  CK(cudaMemsetAsync(e.Linv, 0, sizeof(double) * C * (size_t)(d.gdim / TILE_N) * TILE_N * TILE_N, h->stream));
   e.syrk_ws = nullptr; e.syrk_ws_cap = 0;
   if (d.gmode == BNR_GAMMA_NFORM) {
     // few chains x tiles: the SYRK splits its contraction (see launch_syrk_G).  The split count is fixed per handle
@@ -395,8 +397,13 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     // measured on B200 (round 2, 100-sweep runs): 64 chains of config 3 with 2 / 3 / 4 / 6 / 8 groups -> 10.94 / 10.97 /
     // 11.02 / 11.17 / 11.29 ms per sweep; 32 chains: 2 / 3 / 4 -> 5.87 / 5.86 / 5.96 ms; 8 chains: 2 / 4 / 8 -> 2.02 /
     // 1.95 / 2.16 ms; config 4 (8 chains, split-K SYRK: every group's SYRK fills the GPU by itself): 2 / 4 -> 1.69 / 1.84
-    int ng_auto = d.C >= 24 ? 2 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1));
+    // later in round 2 (look-ahead panel kernel): 8 chains of config 3 with 2 / 3 / 4 / 8 groups -> 1.86 / 1.79 / 1.85 /
+    // 2.05 ms (three uneven groups of 2-3 chains: two concurrent SYRKs then leave ~40 SMs to the third group's panel
+    // chain instead of 4), 16 chains: 2 / 3 / 4 / 8 -> 3.20 / 3.11 / 3.12 / 3.26; config 2 (q-form, no SYRK in the
+    // sweep, pure latency chain): 1 / 2 / 4 / 8 -> 0.340 / 0.342 / 0.344 / 0.350
+    int ng_auto = d.C >= 24 ? 2 : (d.C >= 6 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
     if (d.gmode == BNR_GAMMA_NFORM && d.C >= 4 && syrk_splits(d, d.C) > 1) ng_auto = 2;
+    if (d.gmode == BNR_GAMMA_QFORM && d.C >= 2 && d.C < 24) ng_auto = 2;
     int ng = p->chain_groups > 0 ? p->chain_groups : ng_auto;
     if (ng > MAX_GROUPS) ng = MAX_GROUPS;
     if (ng > d.C) ng = d.C;

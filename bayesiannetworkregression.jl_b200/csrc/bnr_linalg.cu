@@ -593,7 +593,13 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define STAMP(i) do { } while (0)
 #endif
 
-constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB + 64) + 32;
+constexpr size_t POTF2_SMEM = sizeof(double) * ((size_t)PB * PLD + 8 * XD_BLK + PB) + 8 * (4 + PB);
+#ifndef BNR_POTF2_PUBLISH
+#define BNR_POTF2_PUBLISH 8
+#endif
+// the pivot warp publishes its columns in groups of this many: one release-arrive per column cost it ~0.25 us per 32
+// columns more than one per 8 (measured: pivot block 4.2-4.9 / 4.0-4.1 / 3.9 us with 1 / 4 / 8)
+constexpr int POTF2_PUBLISH = BNR_POTF2_PUBLISH;
 constexpr int PU_ROWS = 32;        // k-rows of L(J, J-1) per staged chunk of the in-kernel diagonal update
 static_assert(2 * PU_ROWS * PLD <= 8 * XD_BLK, "the update ring aliases the inverse scratch");
 
@@ -631,6 +637,35 @@ __device__ __forceinline__ void potf2_update_apply(double* A, int lk, int lr, co
   }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Four 8 x 8 output fragments (rows m0.., columns 0..31) of a 32^3 block product on the FP64 tensor cores, operands
+// column-major in shared memory:  c += A[m0.., :] B.   KIND 1: A is lower triangular (k <= m: the k-steps beyond the
+// fragment's rows are skipped), KIND 2: B is lower triangular (k >= n: fragment i starts at k = 8 i), KIND 0: full.
+// The skipped products are exact zeros, so the result does not depend on KIND.
+template <int KIND>
+__device__ __forceinline__ void quad_term(double (&c)[4][2], const double* Aop, int lda, const double* Bop, int ldb,
+                                          int m0, int lk, int lr) {
+  const int k4hi = (KIND == 1) ? (m0 >> 2) + 2 : 8;
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) {
+    if (k4 < k4hi) {
+      const int k = k4 * 4 + lk;
+      const double at = Aop[k * lda + m0 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (KIND != 2 || k4 >= 2 * i) dmma884(c[i][0], c[i][1], Bop[(8 * i + lr) * ldb + k], at);
+    }
+  }
+}
+__device__ __forceinline__ void quad_store(double* dst, int ldd, int m0, double sign, const double (&c)[4][2], int lk, int lr) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<double2*>(dst + (8 * i + lr) * ldd + m0 + 2 * lk) = make_double2(sign * c[i][0], sign * c[i][1]);
+}
+
 // Panel kernel of the blocked Cholesky, one CTA per chain:
 //   (late update)  D = G[J, J] - L[J, J-1] L[J, J-1]'   when `late` (the contributions of the panels before J-1 were
 //                  applied earlier by k_chol_update; L[J, J-1] streams through a two-buffer TMA ring into DMMA fragments)
@@ -643,17 +678,16 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
   double* Xd = sm + PB * PLD;              // [4] inverses of the 32 x 32 diagonal blocks, column stride XD_LD
   double* Tm = Xd + 4 * XD_BLK;            // [4] intermediate products of the inverse
   double* dall = Tm + 4 * XD_BLK;          // [128] reciprocal diagonal of L
-  double* Lcol = dall + PB;                // [2][32] current column of the 32 x 32 factorisation (double-buffered)
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(Lcol + 64);   // [0] block load, [1..2] update ring
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(dall + PB);   // [0] block load, [1..2] update ring
+  unsigned long long* colbar = bar + 4;    // [128] "column j of L is published" (one phase each, one arrival)
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lk = lane & 3, lr = lane >> 2;
   double* Gc = G + (size_t)c * chain_stride;
   double* D = Gc + (size_t)J * PB * N + (size_t)J * PB;
   STAMP(0);
-  if (tid == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
+  if (tid < PB) mbar_init(&colbar[tid], 1);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncthreads();
   // the 128 x 128 block: 16-byte LDGSTS copies by all threads (a 1 KB column = one coalesced request of 64 threads;
   // 128 one-kilobyte bulk copies took 4.4 us here -- the TMA engine accepts ~1 such request per 30 ns)
@@ -717,14 +751,51 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
     __syncthreads();
   }
   STAMP(1);
+  // ---- factor + inverse, software-pipelined over the four 32-wide steps ----
+  // Only the 32 x 32 pivot chain (128 dependent rsqrt steps of ~110 ns) is serial; everything else hangs off it:
+  //   warp 0        pivot warp: factors the 32 x 32 diagonal block of step s in registers and PUBLISHES every finished
+  //                 column of L (written in place + one mbarrier arrival per column).
+  //   warps 1-3     rows below the diagonal block, one thread per row, eliminating column j as soon as it is published
+  //                 (right-looking: the only inputs of column step j are that column of L_ss and its reciprocal pivot), so
+  //                 the rows are complete one column behind the pivot warp instead of a phase after it.
+  //   warp 7        the same elimination on the 32 unit rows e_j: x = e_j L_ss^-T is column j of L_ss^-1 -> Xd[s].
+  //   warp 4        (the pivot warp's scheduler partition: no FP64) stores finished block columns of L and rows of Linv.
+  //   warps 5, 6    + the row warps that have run out of rows: the inverse, bordered by block rows, on the tensor cores:
+  //                   Y(i,j) = sum_{j<=k<i} L(i,k) X(k,j),  X(i,j) = -Xd_i Y(i,j),  X(i,i) = Xd_i = L_ii^-1
+  //                 -- every product except the last block row is ready before the pivot chain ends.
+  // Between steps only the 10 fragments of the NEXT diagonal block are updated by everybody (Tdiag); the rest of the
+  // trailing update runs under the next pivot block (the lock-step rows simply start late and catch up).
+  auto blkA = [&](int i, int j) { return A + (32 * j) * PLD + 32 * i; };        // block (i, j) of the working matrix
+  auto trail = [&](int s, int f0, int f1, int slot, int nslots) {
+    // A[r][cc] -= sum_p L[r][o+p] L[cc][o+p] for the 8 x 8 fragments f0 <= f < f1 of the lower triangle below step s
+    // (fragment f = fr (fr + 1) / 2 + fc, fc <= fr; diagonal fragments are computed whole: what lands above the
+    // diagonal is never read).  f < 10 is the next diagonal block.
+    const int o = s * 32, base = o + 32;
+    const double* P = A + o * PLD + base;             // panel: P[p * PLD + i] = L[base + i][o + p]
+    for (int f = f0 + slot; f < f1; f += nslots) {
+      int fr = 0;
+      while ((fr + 1) * (fr + 2) / 2 <= f) ++fr;
+      const int fc = f - fr * (fr + 1) / 2;
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const int k = k4 * 4 + lk;
+        dmma884(c0, c1, P[k * PLD + fc * 8 + lr], P[k * PLD + fr * 8 + lr]);     // M along the column index cc
+      }
+      double2* dst = reinterpret_cast<double2*>(A + (base + fc * 8 + lr) * PLD + base + fr * 8 + 2 * lk);
+      double2 v = *dst;
+      v.x -= c0; v.y -= c1;
+      *dst = v;
+    }
+  };
   bool bad = false;
   for (int s = 0; s < PB / 32; ++s) {
     const int o = s * 32;
     if (warp == 0) {
       // 32 x 32 Cholesky in registers: lane r holds row o+r (columns o .. o+31); entries above the diagonal are
-      // whatever the block held there and never reach a valid entry.  Column j is broadcast through shared memory
-      // (one store + broadcast loads instead of 31 shuffles), and the next pivot is updated and fetched FIRST so
-      // its rsqrt chain runs under the remaining updates of column j.
+      // whatever the block held there and never reach a valid entry.  Column j is broadcast through its final place in
+      // shared memory, and the next pivot is updated and fetched FIRST so its rsqrt chain runs under the remaining
+      // updates of column j.
       double a[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] = A[(o + j) * PLD + o + lane];
@@ -734,9 +805,8 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
         if (!(djj > 0.0)) bad = true;
         const double inv = rsqrt(djj);
         const double lj = (lane == j) ? djj * inv : a[j] * inv;
-        a[j] = lj;
-        double* lc = Lcol + (j & 1) * 32;
-        lc[lane] = lj;
+        double* lc = A + (o + j) * PLD + o;
+        if (lane >= j) lc[lane] = lj;
         if (lane == j) dall[o + j] = inv;
         if (j + 1 < 32) {
           // next pivot first, without the round trip through shared memory: for the lane that owns row j + 1 the
@@ -745,216 +815,160 @@ __global__ void __launch_bounds__(256) k_potf2_inv(double* __restrict__ G, size_
           djj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
         }
         __syncwarp();
+        if ((j % POTF2_PUBLISH) == POTF2_PUBLISH - 1 && lane == 0)
+          mbar_arrive(&colbar[o + j]);                // release: columns <= j and their reciprocal pivots are visible
         if (j + 1 < 32 && lane != j + 1) a[j + 1] = fma(-lj, lc[j + 1], a[j + 1]);
 #pragma unroll
         for (int cc = j + 2; cc < 32; ++cc) a[cc] -= lj * lc[cc];
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (lane >= j) A[(o + j) * PLD + o + lane] = a[j];
-    }
-    __syncthreads();
-    STAMP(2 + 3 * s);
-    // rows below: x L_ss' = a, thread per row, right-looking (independent FMAs, broadcast reads of L_ss).  Warp 7 runs the
-    // SAME code on the 32 unit rows e_j: x = e_j L_ss^-T is column j of L_ss^-1, so the inverse of the diagonal block
-    // (needed for Linv below) costs no extra phase -- and no extra code: this straight-line solve runs cold from the
-    // instruction cache (~10 cycles per instruction), a separate copy of it for the inverses took 7 us per panel.
-    const int nbelow = PB - (o + 32);
-    const bool inv_row = (warp == 7);
-    if (tid < nbelow || inv_row) {
-      double* row = A + o * PLD + o + 32 + tid;
-      double x[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = inv_row ? ((j == lane) ? 1.0 : 0.0) : row[j * PLD];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const double xj = x[j] * dall[o + j];
-        x[j] = xj;
-#pragma unroll
-        for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PLD + o + k];
+      STAMP(2 + 3 * s);
+    } else {
+      if (s > 0) {
+        trail(s - 1, 10, (PB - o) / 8 * ((PB - o) / 8 + 1) / 2, warp - 1, 7);    // the rest of the previous step's update
+        named_bar_sync(1, 224);
       }
-      if (inv_row) {
+      const int nrow_warps = 3 - s;                   // warps 1 .. nrow_warps own the rows below this step's block
+      if (warp == 7 || warp <= nrow_warps) {
+        const bool inv_row = (warp == 7);
+        double* row = A + o * PLD + o + 32 + (warp - 1) * 32 + lane;
+        double x[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) Xd[s * XD_BLK + lane * XD_LD + j] = (j >= lane) ? x[j] : 0.0;
-      } else {
+        for (int j = 0; j < 32; ++j) x[j] = inv_row ? ((j == lane) ? 1.0 : 0.0) : row[j * PLD];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) row[j * PLD] = x[j];
-      }
-    }
-    __syncthreads();
-    STAMP(3 + 3 * s);
-    // trailing update on the tensor cores: A[r][cc] -= sum_p L[r][o+p] L[cc][o+p] for o+32 <= cc <= r, by 8 x 8
-    // fragments of the lower triangle (diagonal fragments are computed whole; what lands above the diagonal is
-    // never read).  Fragment (fr, fc), fc <= fr; the warps take them round-robin.
-    {
-      const int base = o + 32, nf = (PB - base) / 8, nfrag = nf * (nf + 1) / 2;
-      const double* P = A + o * PLD + base;           // panel: P[p * PLD + i] = L[base + i][o + p]
-      for (int f = warp; f < nfrag; f += 8) {
-        int fr = 0;
-        while ((fr + 1) * (fr + 2) / 2 <= f) ++fr;
-        const int fc = f - fr * (fr + 1) / 2;
-        double c0 = 0.0, c1 = 0.0;
+        for (int j = 0; j < 32; ++j) {
+          if ((j % POTF2_PUBLISH) == 0) mbar_wait(&colbar[o + j + POTF2_PUBLISH - 1], 0);
+          const double xj = x[j] * dall[o + j];
+          x[j] = xj;
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const int k = k4 * 4 + lk;
-          dmma884(c0, c1, P[k * PLD + fc * 8 + lr], P[k * PLD + fr * 8 + lr]);   // M along the column index cc
+          for (int k = j + 1; k < 32; ++k) x[k] -= xj * A[(o + j) * PLD + o + k];
         }
-        double2* dst = reinterpret_cast<double2*>(A + (base + fc * 8 + lr) * PLD + base + fr * 8 + 2 * lk);
-        double2 v = *dst;
-        v.x -= c0; v.y -= c1;
-        *dst = v;
+        if (inv_row) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) Xd[s * XD_BLK + lane * XD_LD + j] = (j >= lane) ? x[j] : 0.0;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) row[j * PLD] = x[j];
+        }
+      } else if (warp == 4) {
+        // finished pieces go to global memory through the TMA engine (one bulk store per lane and column): direct
+        // stores from this warp clogged the memory pipe it shares with the pivot warp (the following diagonal-block
+        // update took 5 us instead of 1)
+        fence_async_smem();                           // the pieces were written through the generic proxy
+        if (s > 0) {
+          // block column s-1 of the factor is final (rows from its diagonal block down)
+          const int ob = o - 32;
+          bulk_s2g(D + (size_t)(ob + lane) * N + ob, A + (ob + lane) * PLD + ob, (unsigned)(PB - ob) * 8u);
+        }
+        if (s == 3) {
+          // rows 0..63 of the inverse are final: X(0,0) = Xd0, X(1,0), X(1,1) = Xd1 (zeros above the diagonal of the
+          // diagonal blocks come from Xd; the zero blocks above them are never written: the buffer is zeroed at creation)
+          double* dst = Linv + ((size_t)c * T + J) * PB * PB;
+          bulk_s2g(dst + (size_t)lane * PB, Xd + lane * XD_LD, 256u);
+          bulk_s2g(dst + (size_t)lane * PB + 32, A + lane * PLD + 32, 256u);
+          bulk_s2g(dst + (size_t)(32 + lane) * PB + 32, Xd + XD_BLK + lane * XD_LD, 256u);
+        }
+        bulk_commit();
+        bulk_wait_read0();                            // the sources may be overwritten after this step's barrier
+      } else if (s > 0) {
+        // the inverse, one block row behind the factorisation.  Slots: warps 5, 6, then the idle row warps 3, 2, 1.
+        const int slot = (warp >= 5) ? warp - 5 : 5 - warp, nslots = 2 + s;
+        double* Tm0 = Tm; double* Tm1 = Tm + XD_BLK; double* Tm2 = Tm + 2 * XD_BLK; double* Tm3 = Tm + 3 * XD_BLK;
+        const double* X0 = Xd; const double* X1 = Xd + XD_BLK; const double* X2 = Xd + 2 * XD_BLK;
+        if (s == 1) {
+          for (int q = slot; q < 4; q += nslots) {                               // Y(1,0) = L(1,0) Xd0
+            double cq[4][2] = {};
+            quad_term<2>(cq, blkA(1, 0), PLD, X0, XD_LD, 8 * q, lk, lr);
+            quad_store(Tm0, XD_LD, 8 * q, 1.0, cq, lk, lr);
+          }
+        } else if (s == 2) {
+          for (int q = slot; q < 8; q += nslots) {
+            const int m0 = 8 * (q & 3);
+            double cq[4][2] = {};
+            if (q < 4) {                                                         // X(1,0) = -Xd1 Y(1,0)   (in place of L(1,0))
+              quad_term<1>(cq, X1, XD_LD, Tm0, XD_LD, m0, lk, lr);
+              quad_store(blkA(1, 0), PLD, m0, -1.0, cq, lk, lr);
+            } else {                                                             // Y(2,1) = L(2,1) Xd1
+              quad_term<2>(cq, blkA(2, 1), PLD, X1, XD_LD, m0, lk, lr);
+              quad_store(Tm2, XD_LD, m0, 1.0, cq, lk, lr);
+            }
+          }
+          named_bar_sync(2, 32 * nslots);
+          for (int q = slot; q < 4; q += nslots) {                               // Y(2,0) = L(2,0) Xd0 + L(2,1) X(1,0)
+            double cq[4][2] = {};
+            quad_term<2>(cq, blkA(2, 0), PLD, X0, XD_LD, 8 * q, lk, lr);
+            quad_term<0>(cq, blkA(2, 1), PLD, blkA(1, 0), PLD, 8 * q, lk, lr);
+            quad_store(Tm1, XD_LD, 8 * q, 1.0, cq, lk, lr);
+          }
+        } else {
+          for (int q = slot; q < 12; q += nslots) {
+            const int m0 = 8 * (q & 3);
+            double cq[4][2] = {};
+            if (q < 8) {                                                         // X(2,j) = -Xd2 Y(2,j), j = 0, 1
+              quad_term<1>(cq, X2, XD_LD, q < 4 ? Tm1 : Tm2, XD_LD, m0, lk, lr);
+              quad_store(blkA(2, q >> 2), PLD, m0, -1.0, cq, lk, lr);
+            } else {                                                             // Y(3,2) = L(3,2) Xd2
+              quad_term<2>(cq, blkA(3, 2), PLD, X2, XD_LD, m0, lk, lr);
+              quad_store(Tm3, XD_LD, m0, 1.0, cq, lk, lr);
+            }
+          }
+          named_bar_sync(2, 32 * nslots);
+          for (int q = slot; q < 8; q += nslots) {
+            const int m0 = 8 * (q & 3);
+            double cq[4][2] = {};
+            if (q < 4) {                                                         // Y(3,0) = L(3,0) Xd0 + L(3,1) X(1,0) + L(3,2) X(2,0)
+              quad_term<2>(cq, blkA(3, 0), PLD, X0, XD_LD, m0, lk, lr);
+              quad_term<0>(cq, blkA(3, 1), PLD, blkA(1, 0), PLD, m0, lk, lr);
+              quad_term<0>(cq, blkA(3, 2), PLD, blkA(2, 0), PLD, m0, lk, lr);
+              quad_store(Tm0, XD_LD, m0, 1.0, cq, lk, lr);
+            } else {                                                             // Y(3,1) = L(3,1) Xd1 + L(3,2) X(2,1)
+              quad_term<2>(cq, blkA(3, 1), PLD, X1, XD_LD, m0, lk, lr);
+              quad_term<0>(cq, blkA(3, 2), PLD, blkA(2, 1), PLD, m0, lk, lr);
+              quad_store(Tm1, XD_LD, m0, 1.0, cq, lk, lr);
+            }
+          }
+        }
       }
     }
-    __syncthreads();
+    fence_async_smem();                               // what this step wrote will be read by warp 4's bulk stores
+    __syncthreads();                                  // step s: pivot block, rows below, Xd[s], side work all done
+    STAMP(3 + 3 * s);
+    if (s + 1 < PB / 32) {
+      trail(s, 0, 10, warp, 8);                       // the next diagonal block
+      __syncthreads();
+    }
     STAMP(4 + 3 * s);
   }
-  if (bad) atomicOr(&status[c], BNR_ST_G_NOTPD_);
-  // the factor goes back to global memory (full columns: the part above the diagonal is never read by anyone), 16 bytes
-  // per thread and store
-  {
-    const int chunk = tid & 63, c0 = tid >> 6;
-#pragma unroll 8
-    for (int i = 0; i < PB / 4; ++i) {
-      const int col = c0 + 4 * i;
-      *reinterpret_cast<double2*>(D + (size_t)col * N + chunk * 2) = *reinterpret_cast<const double2*>(A + col * PLD + chunk * 2);
-    }
+  if (bad && lane == 0) atomicOr(&status[c], BNR_ST_G_NOTPD_);
+  // ---- tail: the last block row of the inverse, X(3,j) = -Xd3 Y(3,j) (in place of L(3,j), which warp 4 has stored) ----
+  for (int q = warp; q < 12; q += 8) {
+    const int m0 = 8 * (q & 3), j = q >> 2;
+    double cq[4][2] = {};
+    quad_term<1>(cq, Xd + 3 * XD_BLK, XD_LD, Tm + (j == 2 ? 3 : j) * XD_BLK, XD_LD, m0, lk, lr);
+    quad_store(blkA(3, j), PLD, m0, -1.0, cq, lk, lr);
   }
+  {
+    // the last diagonal block of the factor (32 x 32; rows 96..127 of columns 96..127)
+    const int col = 96 + (tid >> 3), r = 96 + 4 * (tid & 7);
+    *reinterpret_cast<double2*>(D + (size_t)col * N + r) = *reinterpret_cast<const double2*>(A + col * PLD + r);
+    *reinterpret_cast<double2*>(D + (size_t)col * N + r + 2) = *reinterpret_cast<const double2*>(A + col * PLD + r + 2);
+  }
+  __syncthreads();
   STAMP(14);
-  // ---- inverse, in place ----
-  // (1) the four 32 x 32 diagonal inverses were computed next to the factorisation (warp 7 of the "rows below" pass)
-  __syncthreads();
-  STAMP(15);
-  // (2) off-diagonal 32 x 32 blocks of the inverse by the recursive 2 x 2 block formula
-  //        [[A, 0], [C, B]]^-1 = [[A^-1, 0], [-B^-1 C A^-1, B^-1]],
-  //     first inside the two 64 x 64 diagonal blocks, then for the 64 x 64 block below them: four stages of 32^3
-  //     products on the tensor cores, 8 x 8 output fragments dealt round-robin to the warps.
-  auto blkA = [&](int i, int j) { return A + (32 * j) * PLD + 32 * i; };        // block (i, j) of the working matrix
-  auto put = [&](double* Cb, int ldc, int m0, int n0, double c0, double c1) {
-    *reinterpret_cast<double2*>(Cb + (n0 + lr) * ldc + m0 + 2 * lk) = make_double2(c0, c1);
-  };
-  // stage 1: T_b = L_(2b+1, 2b) Xd_(2b), b = 0, 1        (32 fragments, 4 per warp, computed together)
   {
-    double c4[4][2];
-    const double* Ap[4]; const double* Bp[4];
-    int la[4], lb[4], m0[4], n0[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = warp + 8 * i, b = t >> 4;
-      m0[i] = ((t >> 2) & 3) * 8; n0[i] = (t & 3) * 8;
-      Ap[i] = blkA(2 * b + 1, 2 * b); la[i] = PLD; Bp[i] = Xd + (2 * b) * XD_BLK; lb[i] = XD_LD;
-      c4[i][0] = c4[i][1] = 0.0;
-    }
-    frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) put(Tm + ((warp + 8 * i) >> 4) * XD_BLK, XD_LD, m0[i], n0[i], c4[i][0], c4[i][1]);
-  }
-  __syncthreads();
-  // stage 2: X_(2b+1, 2b) = -Xd_(2b+1) T_b
-  {
-    double c4[4][2];
-    const double* Ap[4]; const double* Bp[4];
-    int la[4], lb[4], m0[4], n0[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = warp + 8 * i, b = t >> 4;
-      m0[i] = ((t >> 2) & 3) * 8; n0[i] = (t & 3) * 8;
-      Ap[i] = Xd + (2 * b + 1) * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + b * XD_BLK; lb[i] = XD_LD;
-      c4[i][0] = c4[i][1] = 0.0;
-    }
-    frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = (warp + 8 * i) >> 4;
-      put(blkA(2 * b + 1, 2 * b), PLD, m0[i], n0[i], -c4[i][0], -c4[i][1]);
-    }
-  }
-  __syncthreads();
-  // stage 3: T2 = C A^-1 with C = blocks (2..3, 0..1):  T2_(i,0) = C_(i,0) X_00 + C_(i,1) X_10,  T2_(i,1) = C_(i,1) X_11
-  //          (64 fragments; every warp takes two fragment positions in each of the four blocks -> equal work;
-  //           the 8 fragments of a warp run as two batches of 4 independent chains, the second product of the
-  //           left-column blocks as a third)
-  // stage 4: X_C = -B^-1 T2:  X_(2,j) = -X_22 T2_(2,j),  X_(3,j) = -(X_32 T2_(2,j) + X_33 T2_(3,j)), j = 0, 1
-#pragma unroll
-  for (int stage = 3; stage <= 4; ++stage) {
-    double c8[8][2];
-    int m8[8], n8[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = warp + 8 * i, fpos = ((t >> 5) << 3) | (t & 7);
-      m8[i] = (fpos >> 2) * 8; n8[i] = (fpos & 3) * 8;
-      c8[i][0] = c8[i][1] = 0.0;
-    }
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      double c4[4][2];
-      const double* Ap[4]; const double* Bp[4];
-      int la[4], lb[4], m0[4], n0[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ii = 4 * half + i, t = warp + 8 * ii, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
-        m0[i] = m8[ii]; n0[i] = n8[ii];
-        c4[i][0] = c4[i][1] = 0.0;
-        if (stage == 3) {
-          if (jb == 0) { Ap[i] = blkA(2 + ib, 0); la[i] = PLD; Bp[i] = Xd; lb[i] = XD_LD; }
-          else { Ap[i] = blkA(2 + ib, 1); la[i] = PLD; Bp[i] = Xd + XD_BLK; lb[i] = XD_LD; }
-        } else {
-          if (ib == 0) { Ap[i] = Xd + 2 * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + jb * XD_BLK; lb[i] = XD_LD; }
-          else { Ap[i] = blkA(3, 2); la[i] = PLD; Bp[i] = Tm + jb * XD_BLK; lb[i] = XD_LD; }
-        }
-      }
-      frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { c8[4 * half + i][0] = c4[i][0]; c8[4 * half + i][1] = c4[i][1]; }
-    }
-    {
-      // second products: stage 3, left-column blocks (jb == 0): += C_(i,1) X_10; stage 4, bottom blocks (ib == 1):
-      // += X_33 T2_(3,j).  With t = warp + 8 i: blk = i & 3, so jb == 0 <=> i even, ib == 1 <=> (i & 2) != 0.
-      double c4[4][2];
-      const double* Ap[4]; const double* Bp[4];
-      int la[4], lb[4], m0[4], n0[4], idx[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ii = (stage == 3) ? 2 * i : (4 * (i >> 1) + 2 + (i & 1));
-        const int t = warp + 8 * ii, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
-        idx[i] = ii; m0[i] = m8[ii]; n0[i] = n8[ii];
-        c4[i][0] = c8[ii][0]; c4[i][1] = c8[ii][1];
-        if (stage == 3) { Ap[i] = blkA(2 + ib, 1); la[i] = PLD; Bp[i] = blkA(1, 0); lb[i] = PLD; }
-        else { Ap[i] = Xd + 3 * XD_BLK; la[i] = XD_LD; Bp[i] = Tm + (2 + jb) * XD_BLK; lb[i] = XD_LD; }
-      }
-      frag_mm32_batch<4>(c4, Ap, la, Bp, lb, m0, n0, lk, lr);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { c8[idx[i]][0] = c4[i][0]; c8[idx[i]][1] = c4[i][1]; }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = warp + 8 * i, blk = (t >> 3) & 3, ib = blk >> 1, jb = blk & 1;
-      if (stage == 3) put(Tm + (2 * ib + jb) * XD_BLK, XD_LD, m8[i], n8[i], c8[i][0], c8[i][1]);
-      else put(blkA(2 + ib, jb), PLD, m8[i], n8[i], -c8[i][0], -c8[i][1]);
-    }
-    __syncthreads();
-  }
-  STAMP(16);
-  // (3) Linv_J goes to global memory straight from the pieces: the diagonal 32 x 32 blocks from Xd, the blocks below them
-  //     from A, exact zeros above the diagonal (the panel solve sums over all 128 k)
-  {
+    // rows 64..127 of Linv_J: X(2,0..1), Xd2 | X(3,0..2), Xd3; the zero blocks above the diagonal are never written
     double* dst = Linv + ((size_t)c * T + J) * PB * PB;
-    const int chunk = tid & 63, c0 = tid >> 6, r = chunk * 2;
-#pragma unroll 8
-    for (int i = 0; i < PB / 4; ++i) {
-      const int cc = c0 + 4 * i;
-      double2 v;
-      if ((r >> 5) == (cc >> 5)) {
-        const double* xd = Xd + (r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31);
-        v.x = (r >= cc) ? xd[0] : 0.0;
-        v.y = (r + 1 >= cc) ? xd[1] : 0.0;
-      } else if (r > cc) {
-        v = *reinterpret_cast<const double2*>(A + cc * PLD + r);
-      } else {
-        v.x = 0.0; v.y = 0.0;
-      }
-      *reinterpret_cast<double2*>(dst + (size_t)cc * PB + r) = v;
+    const int r = 64 + 2 * (tid & 31), c0 = tid >> 5;
+#pragma unroll 4
+    for (int i = 0; i < PB / 8; ++i) {
+      const int cc = c0 + 8 * i;
+      if ((cc >> 5) > (r >> 5)) continue;
+      const double* src = ((r >> 5) == (cc >> 5)) ? Xd + (r >> 5) * XD_BLK + (cc & 31) * XD_LD + (r & 31) : A + cc * PLD + r;
+      *reinterpret_cast<double2*>(dst + (size_t)cc * PB + r) = *reinterpret_cast<const double2*>(src);
     }
   }
+  if (warp == 4) bulk_wait0();                        // this warp's bulk stores have landed
+  STAMP(15);
+  STAMP(16);
   STAMP(17);
 }
 

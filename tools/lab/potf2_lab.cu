@@ -2,6 +2,7 @@
 // event timings of the panel-chain kernels on a synthetic SPD matrix.   nvcc ... -DBNR_POTF2_STAMPS tools/lab/potf2_lab.cu
 #include "../../bayesiannetworkregression.jl_b200/csrc/bnr_linalg.cu"
 #include <cstdio>
+#include <cmath>
 #include <vector>
 namespace bnr { thread_local long long g_launches = 0; }
 using namespace bnr;
@@ -15,6 +16,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&G, sizeof(double) * cs * C + 16384); cudaMalloc(&G0, sizeof(double) * cs * C + 16384);
   cudaMalloc(&Linv, sizeof(double) * (size_t)C * T * PB * PB); cudaMalloc(&status, sizeof(int) * C);
   cudaMemset(status, 0, sizeof(int) * C);
+  cudaMemset(Linv, 0, sizeof(double) * (size_t)C * T * PB * PB);      // the zero blocks of Linv are never written
   std::vector<double> h(cs);
   for (int j = 0; j < N; ++j)
     for (int i = 0; i < N; ++i) h[(size_t)j * N + i] = (i == j) ? N + 1.0 : 0.5 + 0.3 * (((i * 31 + j * 17) % 13) / 13.0);
@@ -34,12 +36,52 @@ int main(int argc, char** argv) {
   for (int J = 0; J < 2; ++J) {
     char nm[64]; snprintf(nm, 64, "k_potf2_inv J=%d late=%d", J, J > 0);
     timeit(nm, [&] { k_potf2_inv<<<C, 256, POTF2_SMEM>>>(G, cs, N, J, Linv, T, status, J > 0); });
+    {
+      // host check of the last chain: factor and inverse of the (late-updated) diagonal block
+      const int cc = C - 1;
+      std::vector<double> Dh((size_t)PB * PB), Lh((size_t)PB * PB, 0.0), Xh((size_t)PB * PB, 0.0), Ld((size_t)PB * PB), Xdv((size_t)PB * PB);
+      for (int j = 0; j < PB; ++j)
+        for (int i = 0; i < PB; ++i) {
+          long double v = h[(size_t)(J * PB + j) * N + J * PB + i];
+          if (J > 0) for (int k = 0; k < PB; ++k) v -= (long double)h[(size_t)((J - 1) * PB + k) * N + J * PB + i] * h[(size_t)((J - 1) * PB + k) * N + J * PB + j];
+          Dh[(size_t)j * PB + i] = (double)v;
+        }
+      for (int j = 0; j < PB; ++j) {
+        long double d = Dh[(size_t)j * PB + j];
+        for (int k = 0; k < j; ++k) d -= (long double)Lh[(size_t)k * PB + j] * Lh[(size_t)k * PB + j];
+        const long double ljj = sqrtl(d);
+        Lh[(size_t)j * PB + j] = (double)ljj;
+        for (int i = j + 1; i < PB; ++i) {
+          long double v = Dh[(size_t)j * PB + i];
+          for (int k = 0; k < j; ++k) v -= (long double)Lh[(size_t)k * PB + i] * Lh[(size_t)k * PB + j];
+          Lh[(size_t)j * PB + i] = (double)(v / ljj);
+        }
+      }
+      for (int j = 0; j < PB; ++j)                       // X = L^-1, column j by forward substitution
+        for (int i = j; i < PB; ++i) {
+          long double v = (i == j) ? 1.0L : 0.0L;
+          for (int k = j; k < i; ++k) v -= (long double)Lh[(size_t)k * PB + i] * Xh[(size_t)j * PB + k];
+          Xh[(size_t)j * PB + i] = (double)(v / Lh[(size_t)i * PB + i]);
+        }
+      cudaMemcpy2D(Ld.data(), PB * 8, G + cc * cs + (size_t)J * PB * N + J * PB, (size_t)N * 8, PB * 8, PB, cudaMemcpyDeviceToHost);
+      cudaMemcpy(Xdv.data(), Linv + ((size_t)cc * T + J) * PB * PB, sizeof(double) * PB * PB, cudaMemcpyDeviceToHost);
+      double eL = 0, eX = 0, eZ = 0, nL = 0, nX = 0;
+      for (int j = 0; j < PB; ++j)
+        for (int i = 0; i < PB; ++i) {
+          if (i >= j) {
+            eL = fmax(eL, fabs(Ld[(size_t)j * PB + i] - Lh[(size_t)j * PB + i])); nL = fmax(nL, fabs(Lh[(size_t)j * PB + i]));
+            eX = fmax(eX, fabs(Xdv[(size_t)j * PB + i] - Xh[(size_t)j * PB + i])); nX = fmax(nX, fabs(Xh[(size_t)j * PB + i]));
+          } else eZ = fmax(eZ, fabs(Xdv[(size_t)j * PB + i]));
+        }
+      printf("    check vs host (long double): factor err %.2e (max %.2e)  inverse err %.2e (max %.2e)  above-diagonal of Linv %.2e\n", eL, nL, eX, nX, eZ);
+    }
 #ifdef BNR_POTF2_STAMPS
     unsigned long long st[64];
     cudaMemcpyFromSymbol(st, g_potf2_stamps, sizeof(st));
-    const char* names[18] = {"start", "load(+late update)", "s0 regchol", "s0 below", "s0 trailing", "s1 regchol", "s1 below",
-                             "s1 trailing", "s2 regchol", "s2 below", "s2 trailing", "s3 regchol", "s3 below", "s3 trailing",
-                             "factor store", "diag inverses", "4 DMMA stages", "copy + Linv store"};
+    const char* names[18] = {"start", "load(+late update)", "s0 pivot block", "s0 wait for the others", "s0 next diag block",
+                             "s1 pivot block", "s1 wait for the others", "s1 next diag block", "s2 pivot block",
+                             "s2 wait for the others", "s2 next diag block", "s3 pivot block", "s3 wait for the others", "-",
+                             "tail: last block row of the inverse", "Linv rows 64.. store", "-", "-"};
     for (int i = 1; i < 18; ++i) printf("    %-22s %7.2f us\n", names[i], (st[i] - st[i - 1]) * 1e-3);
     printf("    total                  %7.2f us\n", (st[17] - st[0]) * 1e-3);
 #endif
