@@ -987,7 +987,7 @@ constexpr size_t small_tile_smem(int rows_i) { return sizeof(double) * ((size_t)
 template <int MODE, int NF>
 __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size_t chain_stride, int N, int jb, int ib_first,
                                                     int nstrip, const double* __restrict__ Bj, size_t bj_chain_stride,
-                                                    int ldj, int kcol0) {
+                                                    int ldj, int kcol0, int tri) {
   extern __shared__ __align__(16) double sm[];
   constexpr int ROWS = NF * 8, LDI = ROWS + 4;       // LDI == 4 mod 16: conflict-free fragment loads
   double* sJ = sm;                                   // [128 k][132]  j operand: sJ[k * SY_LDS + row]
@@ -1000,12 +1000,17 @@ __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size
   // sources (k-major: element (row, k) at base[row + ld * k]); kcol0 = first column of the contributing panel
   const double* srcJ = Bj + (size_t)c * bj_chain_stride;
   const double* srcI = Gc + (size_t)kcol0 * N + i0;
+  // Only the part of the j operand that can reach an output is loaded.  MODE 2: Linv_J is lower triangular (entry
+  // (col, k) with k <= col): k-row k is needed from its own 8-column fragment on.  MODE 1 on the diagonal tile (tri):
+  // only the lower triangle of the tile is ever read, so the strip needs the columns up to its own last row.
+  const int jmax = (MODE == 1 && tri) ? (strip + 1) * ROWS : PB;       // columns of the tile this CTA touches
   {
     const int chunk = tid & 63, r0 = tid >> 6;       // j operand: 128 k-rows of 64 16-byte chunks
 #pragma unroll 8
     for (int i = 0; i < PB / 4; ++i) {
       const int k = r0 + 4 * i;
-      cp_async16(sJ + k * SY_LDS + chunk * 2, srcJ + (size_t)k * ldj + chunk * 2);
+      const bool need = (MODE == 2) ? (chunk >= 4 * (k >> 3)) : (2 * chunk < jmax);
+      if (need) cp_async16(sJ + k * SY_LDS + chunk * 2, srcJ + (size_t)k * ldj + chunk * 2);
     }
     constexpr int CPR = ROWS / 2;                    // 16-byte chunks per k-row of the i operand
     for (int id = tid; id < PB * CPR; id += 256) {
@@ -1018,14 +1023,17 @@ __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size
   const int lim0 = 2 * f0 + 2, lim1 = 2 * f1 + 2;    // MODE 2: k4-steps that can still reach the column fragment
   const int j0 = jb * PB;
   double acc[2][NF][2];
+  const bool on0 = f0 * 8 < jmax, on1 = f1 * 8 < jmax;   // column fragments inside the needed part (always, unless tri)
   if (MODE == 1) {                                   // in place: start from the tile's current values
 #pragma unroll
     for (int mf = 0; mf < 2; ++mf) {
       const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
+      if (mf == 0 ? on0 : on1) {
 #pragma unroll
-      for (int nf = 0; nf < NF; ++nf) {
-        const double2 v = *reinterpret_cast<const double2*>(Gc + (size_t)j * N + i0 + nf * 8 + 2 * lk);
-        acc[mf][nf][0] = v.x; acc[mf][nf][1] = v.y;
+        for (int nf = 0; nf < NF; ++nf) {
+          const double2 v = *reinterpret_cast<const double2*>(Gc + (size_t)j * N + i0 + nf * 8 + 2 * lk);
+          acc[mf][nf][0] = v.x; acc[mf][nf][1] = v.y;
+        }
       }
     }
   } else {
@@ -1036,13 +1044,20 @@ __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size
   }
   cp_async_wait<0>();
   __syncthreads();
+  if (MODE == 1 && !on0) return;                     // (f0 < f1: nothing of this warp lies in the lower triangle)
 #pragma unroll 4
   for (int k4 = 0; k4 < PB / 4; ++k4) {
     const int kr = k4 * 4 + lk;
     const double* rj = sJ + kr * SY_LDS + lr;
     const double* ri = sI + kr * LDI + lr;
-    double af0 = rj[f0 * 8], af1 = rj[f1 * 8];
-    if (MODE == 1) { af0 = neg_bits(af0); af1 = neg_bits(af1); }
+    double af0 = 0.0, af1 = 0.0;
+    if (MODE == 2) {                                 // (entries with k beyond the fragment's reach were not loaded)
+      if (k4 < lim0) af0 = rj[f0 * 8];
+      if (k4 < lim1) af1 = rj[f1 * 8];
+    } else {
+      af0 = neg_bits(rj[f0 * 8]);
+      if (on1) af1 = neg_bits(rj[f1 * 8]);
+    }
     double bf[NF];
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf) bf[nf] = ri[nf * 8];
@@ -1059,13 +1074,14 @@ __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size
 #pragma unroll
       for (int nf = 0; nf < NF; ++nf) {
         dmma884(acc[0][nf][0], acc[0][nf][1], af0, bf[nf]);
-        dmma884(acc[1][nf][0], acc[1][nf][1], af1, bf[nf]);
+        if (on1) dmma884(acc[1][nf][0], acc[1][nf][1], af1, bf[nf]);
       }
     }
   }
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf) {
     const int j = j0 + (mf == 0 ? f0 : f1) * 8 + lr;
+    if (mf == 1 && !on1) continue;
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf)
       *reinterpret_cast<double2*>(Gc + (size_t)j * N + i0 + nf * 8 + 2 * lk) = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
@@ -1361,6 +1377,8 @@ void linalg_setup() {
   cudaFuncSetAttribute(k_bwd_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_small_tile<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(32));
   cudaFuncSetAttribute(k_small_tile<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(32));
+  cudaFuncSetAttribute(k_small_tile<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(16));
+  cudaFuncSetAttribute(k_small_tile<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(16));
   cudaFuncSetAttribute(k_small_tile<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(64));
   cudaFuncSetAttribute(k_small_tile<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_tile_smem(64));
 }
@@ -1543,23 +1561,43 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
     dim3 g(d.C, rows * ns);
     const double* Lj = e.Linv + (size_t)J * PB * PB;
     ++g_launches;
-    if (small_tiles && ns == 4)
-      k_small_tile<2, 4><<<g, 256, small_tile_smem(32), st>>>(e.G, cs, N, J, ib_first, 4, Lj, ls, PB, J * PB);
+    if (small_tiles && ns == 8)
+      k_small_tile<2, 2><<<g, 256, small_tile_smem(16), st>>>(e.G, cs, N, J, ib_first, 8, Lj, ls, PB, J * PB, 0);
+    else if (small_tiles && ns == 4)
+      k_small_tile<2, 4><<<g, 256, small_tile_smem(32), st>>>(e.G, cs, N, J, ib_first, 4, Lj, ls, PB, J * PB, 0);
     else if (small_tiles && ns == 2)
-      k_small_tile<2, 8><<<g, 256, small_tile_smem(64), st>>>(e.G, cs, N, J, ib_first, 2, Lj, ls, PB, J * PB);
+      k_small_tile<2, 8><<<g, 256, small_tile_smem(64), st>>>(e.G, cs, N, J, ib_first, 2, Lj, ls, PB, J * PB, 0);
     else
       k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM, st>>>(e.G, cs, N, m + 1, J, ib_first, Lj, ls, ns);
   };
+  // The late part of the diagonal tile (J+1, J+1) -- the contribution of panel J -- either runs inside k_potf2_inv
+  // (one SM: ~12 us of DMMA) or, when the chains are few enough for 4-8 CTAs per tile, as its own strip kernel Ud(J)
+  // right after T1(J) (~5 us), with T1 itself cut into as many strips.
+  static const int ud_knob = getenv("BNR_CHOL_UD") ? atoi(getenv("BNR_CHOL_UD")) : -1;     // tuning knob: 0 off, 4 / 8 strips
+  // (measured: config 2 0.320 -> 0.300 ms, config 4 1.684 -> 1.666 ms; with a chain group's SYRK competing for the SMs
+  //  -- 8 / 16 chains of config 3 -- the extra CTAs wait for SMs and the in-kernel update stays ahead: 1.770 vs 1.782 ms)
+  const bool quiet = d.gmode == 2 || e.syrk_ws != nullptr;          // no full-size SYRK CTAs of other groups around
+  int ud = (small_tiles && quiet) ? (d.C_total * 8 <= 148 ? 8 : (d.C_total * 4 <= 148 ? 4 : 0)) : 0;
+  if (ud_knob == 0 || ud_knob == 4 || ud_knob == 8) ud = small_tiles ? ud_knob : 0;
   for (int J = 0; J < T; ++J) {
     const bool has_side = J + 2 < T;
-    if (fork && J >= 2) cudaStreamWaitEvent(s, evE[J - 2], 0);
-    ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status, J > 0 ? 1 : 0);
+    if (fork && J >= 2 && !ud) cudaStreamWaitEvent(s, evE[J - 2], 0);
+    ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status, (J > 0 && !ud) ? 1 : 0);
     if (fork && has_side) cudaEventRecord(evP[J], s);
     if (J + 1 < T) {
       if (fork && J >= 1 && J + 1 < T) cudaStreamWaitEvent(s, evL[J - 1], 0);
-      const int ns1 = strips(1);
+      const int ns1 = ud ? ud : strips(1);
       launch_trsm(J, J + 1, 1, ns1, s);
       if (fork && has_side) cudaEventRecord(evT[J], s);
+      if (ud) {
+        // Ud(J): tile (J+1, J+1) -= L[J+1, J] L[J+1, J]' (lower triangle), after the early panels 0..J-1 (Uearly(J-1))
+        if (fork && J >= 1) cudaStreamWaitEvent(s, evE[J - 1], 0);
+        dim3 gd(d.C, ud);
+        const double* Lt = e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB;
+        ++g_launches;
+        if (ud == 8) k_small_tile<1, 2><<<gd, 256, small_tile_smem(16), s>>>(e.G, cs, N, J + 1, J + 1, 8, Lt, cs, N, J * PB, 1);
+        else k_small_tile<1, 4><<<gd, 256, small_tile_smem(32), s>>>(e.G, cs, N, J + 1, J + 1, 4, Lt, cs, N, J * PB, 1);
+      }
     }
     if (has_side) {
       const int rows = T - J - 2;                   // row blocks J+2 .. T-1
@@ -1570,9 +1608,9 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
       if (fork) cudaStreamWaitEvent(side, evT[J], 0);
       ++g_launches;
       if (small_tiles && ns2 == 4)
-        k_small_tile<1, 4><<<g2, 256, small_tile_smem(32), side>>>(e.G, cs, N, J + 1, J + 2, 4, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB);
+        k_small_tile<1, 4><<<g2, 256, small_tile_smem(32), side>>>(e.G, cs, N, J + 1, J + 2, 4, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB, 0);
       else if (small_tiles && ns2 == 2)
-        k_small_tile<1, 8><<<g2, 256, small_tile_smem(64), side>>>(e.G, cs, N, J + 1, J + 2, 2, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB);
+        k_small_tile<1, 8><<<g2, 256, small_tile_smem(64), side>>>(e.G, cs, N, J + 1, J + 2, 2, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB, 0);
       else
         k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1, PB / SY_BK, J + 1, J + 2, ns2);
       if (fork) cudaEventRecord(evL[J], side);

@@ -1,7 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/../.."
-T=${TAG:-r2l}
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
+T=${TAG:-r2m}
 B="python bench.py --no-cpu-baseline --no-other-configs --no-strong --ess-draws 0 --steps 100"
 run() { tag=$1; shift; timeout 200 "$@" > gpurun_out/${T}_$tag.json 2> gpurun_out/${T}_$tag.err; python - <<PY
 import json
@@ -11,10 +10,12 @@ try:
 except Exception as ex: print("$tag", "failed", ex)
 PY
 }
-for ud in 8 4 0; do
-BNR_CHOL_UD=$ud run x8_ud$ud $B --config c3 --chains 8
-BNR_CHOL_UD=$ud run x16_ud$ud $B --config c3 --chains 16
-BNR_CHOL_UD=$ud run c2_ud$ud $B --config c2
-BNR_CHOL_UD=$ud run c4_ud$ud $B --config c4
+for same in 0 1; do
+if [ $same = 1 ]; then export BNR_SIDE_HI_SAME=1; fi
+run c2_same$same $B --config c2
+run c4_same$same $B --config c4
+run x8_same$same $B --config c3 --chains 8
+run x16_same$same $B --config c3 --chains 16
+run c5_same$same $B --config c5
+run c3_same$same $B --config c3
 done
-python tools/timeline.py --config c2 --chain-groups 1 --sweeps 2 --out gpurun_out/${T}_tl_c2_g1.txt 2>/dev/null
