@@ -401,7 +401,9 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
     // 2.05 ms (three uneven groups of 2-3 chains: two concurrent SYRKs then leave ~40 SMs to the third group's panel
     // chain instead of 4), 16 chains: 2 / 3 / 4 / 8 -> 3.20 / 3.11 / 3.12 / 3.26; config 2 (q-form, no SYRK in the
     // sweep, pure latency chain): 1 / 2 / 4 / 8 -> 0.340 / 0.342 / 0.344 / 0.350
-    int ng_auto = d.C >= 24 ? 2 : (d.C >= 6 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1)));
+    // with the forked Cholesky updates at the panel chain's priority: 64 chains 2 / 3 / 4 / 5 / 6 groups -> 10.89 / 10.74 /
+    // 10.80 / 10.89 / 10.95 ms; 32 chains 2 / 3 -> 5.76 / 5.52; config 5 (128 chains) 2 / 3 -> 1.80 / 1.77
+    int ng_auto = d.C >= 6 ? 3 : (d.C >= 4 ? 4 : (d.C >= 2 ? 2 : 1));
     if (d.gmode == BNR_GAMMA_NFORM && d.C >= 4 && syrk_splits(d, d.C) > 1) ng_auto = 2;
     if (d.gmode == BNR_GAMMA_QFORM && d.C >= 2 && d.C < 24) ng_auto = 2;
     int ng = p->chain_groups > 0 ? p->chain_groups : ng_auto;

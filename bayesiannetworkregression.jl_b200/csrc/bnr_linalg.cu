@@ -1513,16 +1513,22 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
   if (!latency) {
     // ---- (A) ----
     const bool can_fork = !serial && fj.side != nullptr;
+    // The forked updates run at the panel chain's priority.  With another chain group's SYRK resident (600 us CTAs that
+    // give an SM back every ~4 us) every dependent kernel has to re-acquire its SMs one by one; on the SYRK's own
+    // priority level they queued behind ALL its pending CTAs and the factorisation only ran in the SYRK's last wave
+    // (timeline in profiles/r02_timeline_c3.txt: 1 ms per sweep without any SYRK CTA resident).
+    static const bool a_lo = getenv("BNR_CHOL_A_SIDE_LO") != nullptr;      // knob: the old low-priority branch
+    cudaStream_t sideA = (!a_lo && fj.side_hi) ? fj.side_hi : fj.side;
     for (int J = 0; J < T; ++J) {
       const bool fork = can_fork && J > 0 && J + 1 < T;
       if (J > 0) {
         const int nk = J * PB / SY_BK;
         if (fork) {
           cudaEventRecord(fj.fork, s);
-          cudaStreamWaitEvent(fj.side, fj.fork, 0);
+          cudaStreamWaitEvent(sideA, fj.fork, 0);
           dim3 g2(d.C, T - J - 1);
-          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, fj.side>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J + 1, 1);
-          cudaEventRecord(fj.join, fj.side);
+          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, sideA>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J + 1, 1);
+          cudaEventRecord(fj.join, sideA);
           dim3 g1(d.C, 1);
           ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J, 1);
         } else {
