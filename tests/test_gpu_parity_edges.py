@@ -209,3 +209,25 @@ def test_sample_beta_degenerate_arms(bnr, a_delta, b_delta, xi_val, want):
             assert (a, b) == (a_delta + V * xi_val, b_delta + V * (1 - xi_val))
             ref = O.update_Delta(np.full(V, xi_val), a_delta, b_delta, 1.0, 1.0)
             assert ref["Delta"] == want
+
+
+@pytest.mark.parametrize("mode", ["nform", "qform"])
+def test_lost_positive_definiteness_is_flagged(bnr, mode):
+    """The reference's cholesky(...) throws PosDefException when X D X' + I (src/gibbs.jl:434) is not positive definite;
+    the engine cannot throw from a kernel: the panel kernel meets a non-positive pivot and sets BNR_ST_G_NOTPD for that
+    chain only (negative scales S make the matrix of chain 0 indefinite; chain 1 stays clean)."""
+    V, R, n, C, K = 8, 3, 40, 2, 8
+    X, y = make_problem(9, V, R, n)
+    rng = np.random.default_rng(12)
+    with bnr.Engine(X, y, R, num_chains=C, seed=5, gig_inject_len=K, gamma_mode=mode) as eng:
+        states = [random_state(rng, V, R) for _ in range(C)]
+        # n-form: G = I - 100 X X';  q-form: P = (X'X - 1000 I) / tau2
+        states[0]["S"] = np.full_like(states[0]["S"], -100.0 if mode == "nform" else -1e-3)
+        for c, st in enumerate(states):
+            eng.set_state_dict(c, st)
+        inj = np.stack([sweep_injection(rng, n, V, R, K)[0] for _ in range(C)])
+        eng.set_injection(inj)
+        eng.step("gamma")
+        st = eng.status()
+        assert st[0] & 4, st                                   # BNR_ST_G_NOTPD
+        assert not (st[1] & 4), st
