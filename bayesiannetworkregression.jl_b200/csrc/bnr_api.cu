@@ -297,6 +297,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   CK(cudaEventCreate(&h->ev0));
   CK(cudaEventCreate(&h->ev1));
   linalg_setup();
+  if (!tmap_setup()) return fail(BNR_ECUDA, "cuTensorMapEncodeTiled is not available from this driver (TMA tensor maps are required)");
   small_kernels_setup();
 
   Engine& e = h->e;

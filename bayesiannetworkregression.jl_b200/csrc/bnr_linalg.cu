@@ -5,7 +5,10 @@
 //   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
 //   X v, X' a4 (all chains at once)   -> k_xmma (tall-skinny DMMA GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <cuda.h>
 #include "bnr_engine.cuh"
 #include "bnr_kernels.h"
 
@@ -53,6 +56,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "bra WAIT_LOOP;\n"
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 2-D tiled TMA load (SASS: UTMALDG): one request moves a whole (box_inner rows) x (16 k) operand tile; the box is
+// 4 rows wider than the tile, which IS the shared-memory padding (row pitch == 4 mod 16 doubles: conflict-free fragments)
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(smem_dst)), "l"((unsigned long long)tm), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 // contiguous global -> shared copy by the TMA engine, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
@@ -199,11 +208,11 @@ __device__ __forceinline__ void syrk_diag_tile(const double* smem, unsigned long
 // the zero padding of n up to a multiple of 128 costs no tensor work.
 template <int MODE, int NF>
 __device__ __forceinline__ void syrk_strip_frags(const double* sj, const double* si, const double* ss, int k4,
-                                                 int f0, int f1, int lk, int lr,
+                                                 int f0, int f1, int lk, int lr, int ldi,
                                                  double (&af)[2], double (&bf)[NF]) {
   const int kr = k4 * 4 + lk;
   const double* rj = sj + kr * SY_LDS + lr;
-  const double* ri = si + kr * SY_LDS + lr;
+  const double* ri = si + kr * ldi + lr;
   if (MODE == 0) {
     const double sk = ss[kr];
     af[0] = rj[f0 * 8] * sk;
@@ -225,7 +234,7 @@ __device__ __forceinline__ void syrk_strip_frags(const double* sj, const double*
 template <int MODE, int NF>
 __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned long long* full,
                                                 unsigned long long* empty, int nk, int warp, int lk, int lr, int lane,
-                                                double* __restrict__ Cc, int np, int i0, int j0) {
+                                                double* __restrict__ Cc, int np, int i0, int j0, int ldi) {
   double acc[2][NF][2];
   const int f0 = (MODE == 2) ? warp : 2 * warp, f1 = (MODE == 2) ? 15 - warp : 2 * warp + 1;
   if (MODE == 1) {
@@ -249,17 +258,17 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
   double af[2][2], bf[2][NF];
   mbar_wait(&full[0], 0);
   const double* sj = smem;
-  syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, af[0], bf[0]);
+  syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, ldi, af[0], bf[0]);
   for (int kt = 0; kt < nk; ++kt) {
 #pragma unroll
     for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
       const int cur = k4 & 1, nxt = cur ^ 1;
       if (k4 + 1 < SY_BK / 4) {
-        syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, k4 + 1, f0, f1, lk, lr, af[nxt], bf[nxt]);
+        syrk_strip_frags<MODE, NF>(sj, sj + SY_BK * SY_LDS, sj + 2 * SY_BK * SY_LDS, k4 + 1, f0, f1, lk, lr, ldi, af[nxt], bf[nxt]);
       } else if (kt + 1 < nk) {
         mbar_wait(&full[(kt + 1) % SY_STAGES], ((kt + 1) / SY_STAGES) & 1);
         const double* nj = smem + (size_t)((kt + 1) % SY_STAGES) * SY_STAGE_DBL;
-        syrk_strip_frags<MODE, NF>(nj, nj + SY_BK * SY_LDS, nj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, af[nxt], bf[nxt]);
+        syrk_strip_frags<MODE, NF>(nj, nj + SY_BK * SY_LDS, nj + 2 * SY_BK * SY_LDS, 0, f0, f1, lk, lr, ldi, af[nxt], bf[nxt]);
       }
       if (MODE == 2) {
         const int k4g = kt * (SY_BK / 4) + k4;
@@ -298,13 +307,14 @@ __device__ __forceinline__ void syrk_strip_tile(const double* smem, unsigned lon
   }
 }
 
+// Operands arrive as tensor-map boxes: the j operand through tmj at (row jx, k-row jy0 + 16 kt), the i operand through
+// tmi at (row i0, k-row iy0 + 16 kt); jy0 / iy0 carry the chain, the first contributing column and the k-split offset.
 template <int MODE>
 __device__ __forceinline__ void
-syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const double* __restrict__ scale,
+syrk_body(const CUtensorMap* tmj, const CUtensorMap* tmi, int jy0, int iy0, const double* __restrict__ scale,
           size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
-          double diag_add, const double* __restrict__ Bop = nullptr, size_t b_chain_stride = 0, int part = 0,
-          int nstrip = 1) {
-  extern __shared__ __align__(16) double smem[];
+          double diag_add, int part = 0, int nstrip = 1) {
+  extern __shared__ __align__(128) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -341,14 +351,12 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   const int rows_i = SY_BT / nstrip;
   const int i0 = ib * SY_BT + strip * rows_i, j0 = jb * SY_BT;
   const bool diag = (ib == jb) && nstrip == 1;
-  const double* Ac = A + (size_t)c * a_chain_stride;
   const double* sc = (MODE == 0) ? scale + (size_t)c * scale_stride : nullptr;
   // operand sources (k-major: element (row, k) at base[row + ld * k]).  MODE 0 / 1: both operands are row blocks of
   // the same matrix.  MODE 2: the i operand is block column J of C itself (rows i0.., k = the 128 columns of the
   // panel), the j operand is the 128 x 128 inverse of the diagonal block (ld = 128, rows 0..127).
-  const double* opj = (MODE == 2) ? Bop + (size_t)c * b_chain_stride : Ac + j0;
-  const double* opi = (MODE == 2) ? Ac + (size_t)j0 * ld + i0 : Ac + i0;
-  const int ldj = (MODE == 2) ? SY_BT : ld;
+  const int jx = (MODE == 2) ? 0 : j0;
+  const int ldi = (MODE == 0) ? SY_LDS : rows_i + 4;   // row pitch of the i operand in shared memory = its box width
 
   if (tid == 0) {
     for (int s = 0; s < SY_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -360,7 +368,10 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
     // ---------------- producer warpgroup: hands its registers to the consumers, one lane drives the TMA engine ----
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(SY_PRODUCER_REGS));
     if (warp == 8 && lane == 0) {
-      const unsigned bytes = SY_BK * SY_BT * 8u + (diag ? 0u : SY_BK * (unsigned)rows_i * 8u) + (MODE == 0 ? SY_BK * 8u : 0u);
+      // three requests per stage (two operand boxes + the 16 scales); the first version issued one 1 KB bulk copy per
+      // k-row and operand -- 33 requests, ~1 us per stage at the TMA engine's ~30 ns per request, which bounded every
+      // tile with less than ~1 us of DMMA work per stage (row strips, tiles of a short last row block)
+      const unsigned bytes = SY_BK * SY_LDS * 8u + (diag ? 0u : SY_BK * (unsigned)ldi * 8u) + (MODE == 0 ? SY_BK * 8u : 0u);
       for (int kt = 0; kt < nk; ++kt) {
         const int stage = kt % SY_STAGES;
         const unsigned ph = (kt / SY_STAGES) & 1;
@@ -368,13 +379,8 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
         double* sj = smem + (size_t)stage * SY_STAGE_DBL;
         double* si = sj + SY_BK * SY_LDS;
         mbar_expect_tx(&full[stage], bytes);
-        const double* gj = opj + (size_t)kt * SY_BK * ldj;
-        const double* gi = opi + (size_t)kt * SY_BK * ld;
-#pragma unroll 4
-        for (int kr = 0; kr < SY_BK; ++kr) {
-          bulk_g2s(sj + kr * SY_LDS, gj + (size_t)kr * ldj, SY_BT * 8, &full[stage]);
-          if (!diag) bulk_g2s(si + kr * SY_LDS, gi + (size_t)kr * ld, rows_i * 8, &full[stage]);
-        }
+        tma_load_2d(sj, tmj, jx, jy0 + kt * SY_BK, &full[stage]);
+        if (!diag) tma_load_2d(si, tmi, i0, iy0 + kt * SY_BK, &full[stage]);
         if (MODE == 0) bulk_g2s(si + SY_BK * SY_LDS, sc + kt * SY_BK, SY_BK * 8, &full[stage]);
       }
     }
@@ -417,12 +423,12 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
   // (at least 4 row fragments: fewer template instances; the extra fragments are zero-padding rows of the last block)
   if (nfv < 4) nfv = 4;
   switch (nfv) {
-#define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
+#define BNR_STRIP_CASE(NF) case NF: syrk_strip_tile<MODE, NF>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0, ldi); break;
     BNR_STRIP_CASE(4) BNR_STRIP_CASE(5) BNR_STRIP_CASE(6)
     BNR_STRIP_CASE(7) BNR_STRIP_CASE(8) BNR_STRIP_CASE(9) BNR_STRIP_CASE(10) BNR_STRIP_CASE(11) BNR_STRIP_CASE(12)
     BNR_STRIP_CASE(13) BNR_STRIP_CASE(14) BNR_STRIP_CASE(15)
 #undef BNR_STRIP_CASE
-    default: syrk_strip_tile<MODE, 16>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0); break;
+    default: syrk_strip_tile<MODE, 16>(smem, full, empty, nk, warp, lk, lr, lane, Cc, np, i0, j0, ldi); break;
   }
 }
 
@@ -430,16 +436,16 @@ syrk_body(const double* __restrict__ A, size_t a_chain_stride, int ld, const dou
 // ws[c][z - 1] (split 0 writes G itself, identity included); k_syrk_splitk_reduce adds them in a fixed order.  Used
 // when chains x tiles cannot fill the SMs (few chains, large q: BASELINE config 4).
 __global__ void __launch_bounds__(SY_THREADS, 1)
-k_gram_syrk(const double* __restrict__ X, int ld, const double* __restrict__ scale, size_t scale_stride,
+k_gram_syrk(const __grid_constant__ CUtensorMap tmX, const double* __restrict__ scale, size_t scale_stride,
             double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk, double diag_add,
             int nk_split, double* __restrict__ ws, int ws_cap) {
   const int z = blockIdx.z;
   if (z == 0) {
-    syrk_body<0>(X, 0, ld, scale, scale_stride, G, g_chain_stride, np, nvalid, nk < nk_split ? nk : nk_split, 0, diag_add);
+    syrk_body<0>(&tmX, &tmX, 0, 0, scale, scale_stride, G, g_chain_stride, np, nvalid, nk < nk_split ? nk : nk_split, 0, diag_add);
   } else {
     const int kt0 = z * nk_split;
     const int nkl = (nk - kt0) < nk_split ? (nk - kt0) : nk_split;
-    syrk_body<0>(X + (size_t)kt0 * SY_BK * ld, 0, ld, scale + (size_t)kt0 * SY_BK, scale_stride,
+    syrk_body<0>(&tmX, &tmX, kt0 * SY_BK, kt0 * SY_BK, scale + (size_t)kt0 * SY_BK, scale_stride,
                  ws + (size_t)(z - 1) * g_chain_stride, (size_t)ws_cap * g_chain_stride, np, nvalid, nkl, 0, 0.0);
   }
 }
@@ -465,19 +471,24 @@ __global__ void __launch_bounds__(256) k_syrk_splitk_reduce(double* __restrict__
 // G[ib, jb] -= sum_k P[ib, k] P[jb, k]' for the row blocks ib = ib_first, ib_first + 1, ... (grid.y of them) of block
 // column jb; P points at the first of the nk * 16 columns of the factor that contribute (the caller offsets it), so a
 // launch applies any contiguous range of panels.
+// (tmJ: the chain-stacked matrix {rows, columns x chains} with 132-row boxes; tmI: the same with boxes as wide as a row
+//  strip + 4; kcol0: first contributing column)
 __global__ void __launch_bounds__(SY_THREADS, 1)
-k_chol_update(const double* __restrict__ P, size_t chain_stride, int ld, double* __restrict__ G, int np, int nvalid,
-              int nk, int jb, int ib_first, int nstrip) {
-  syrk_body<1>(P, chain_stride, ld, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, nullptr, 0, ib_first, nstrip);
+k_chol_update(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, int kcol0,
+              double* __restrict__ G, size_t chain_stride, int np, int nvalid, int nk, int jb, int ib_first, int nstrip) {
+  const int y0 = (int)blockIdx.x * np + kcol0;
+  syrk_body<1>(&tmJ, &tmI, y0, y0, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, ib_first, nstrip);
 }
 
 // panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I = ib_first, ... (in place: a CTA
-// has consumed its whole tile through the ring before the first store)
+// has consumed its whole tile through the ring before the first store).  tmL: the stacked inverses {128, 128 x panels x
+// chains}; tmI as above.
 __global__ void __launch_bounds__(SY_THREADS, 1)
-k_trsm_dmma(double* __restrict__ G, size_t chain_stride, int np, int nvalid, int jb, int ib_first,
-            const double* __restrict__ Linv, size_t linv_chain_stride, int nstrip) {
-  syrk_body<2>(G, chain_stride, np, nullptr, 0, G, chain_stride, np, nvalid, SY_BT / SY_BK, jb, 0.0, Linv,
-               linv_chain_stride, ib_first, nstrip);
+k_trsm_dmma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmI, double* __restrict__ G,
+            size_t chain_stride, int np, int nvalid, int jb, int ib_first, int nstrip) {
+  const int T = np / SY_BT;
+  syrk_body<2>(&tmL, &tmI, ((int)blockIdx.x * T + jb) * SY_BT, (int)blockIdx.x * np + jb * SY_BT, nullptr, 0, G, chain_stride,
+               np, nvalid, SY_BT / SY_BK, jb, 0.0, ib_first, nstrip);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1387,6 +1398,42 @@ void linalg_setup() {
 // tile over the whole contraction: 0.7 ms at q = 5050, 2.7 ms at q = 20100) is too coarse a unit of work to balance over
 // 148 SMs, so the contraction is cut into up to 8 pieces of at least 24 k-steps.  The count depends on the handle's chain
 // count only (not on the chain groups, which each launch a part of the chains).
+// ---- tensor maps (host): a k-major operand {rows (contiguous), k-rows} with boxes of box_rows x 16 ----
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn g_tmap_encode = nullptr;
+bool tmap_setup() {
+  if (g_tmap_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+      qr != cudaDriverEntryPointSuccess || !fn)
+    return false;
+  g_tmap_encode = (TmapEncodeFn)fn;
+  return true;
+}
+// rows beyond `rows` (the box is 4 rows wider than a tile) and k-rows beyond `krows` read as zeros
+static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  const cuuint64_t dims[2] = {rows, krows};
+  const cuuint64_t strides[1] = {ld * sizeof(double)};
+  const cuuint32_t box[2] = {box_rows, (cuuint32_t)SY_BK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = (tmap_setup() ? g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
+                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                             : CUDA_ERROR_NOT_SUPPORTED);
+  if (r != CUDA_SUCCESS) {
+    // (bnr_create has already checked tmap_setup(); a failure here is a programming error of the caller's geometry)
+    fprintf(stderr, "[bnr] cuTensorMapEncodeTiled failed (%d) for a %llu x %llu operand, box %u x %d\n", (int)r,
+            (unsigned long long)rows, (unsigned long long)krows, box_rows, SY_BK);
+    abort();
+  }
+  return m;
+}
+
 int syrk_splits(const Dims& d, int C) {
   const int T = d.np / SY_BT, tiles = T * (T + 1) / 2, nk = d.qp / SY_BK;
   if (const char* ov = getenv("BNR_SYRK_SPLITS")) {                       // tuning knob
@@ -1416,7 +1463,8 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
   dim3 grid(d.C, T * (T + 1) / 2, ns);
 #endif
   const size_t gs = (size_t)d.np * d.np;
-  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(e.X, d.np, e.S, (size_t)d.qp, e.G, gs, d.np, d.n, nk, 1.0,
+  const CUtensorMap tmX = make_map(e.X, d.np, d.qp, d.np, SY_LDS);
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(tmX, e.S, (size_t)d.qp, e.G, gs, d.np, d.n, nk, 1.0,
                                                             nk_split, e.syrk_ws, e.syrk_ws_cap);
   if (ns > 1) {
     dim3 g2(T * (T + 1) / 2 * 8, d.C);
@@ -1436,7 +1484,8 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
 void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s) {
   const int T = d.qp / SY_BT;
   dim3 grid(1, T * (T + 1) / 2);
-  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(XT, d.qp, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0,
+  const CUtensorMap tmXT = make_map(XT, d.qp, d.np, d.qp, SY_LDS);
+  ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(tmXT, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0,
                                                             d.np / SY_BK, nullptr, 0);
 }
 
@@ -1509,6 +1558,13 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
   static const int forced = getenv("BNR_CHOL_SCHEDULE") ? atoi(getenv("BNR_CHOL_SCHEDULE")) : 0;   // 1 = (A), 2 = (B)
   const bool latency = forced ? forced == 2 : (long long)d.C_total * (T - 1) <= 128;
   ++g_launches; k_augment<<<d.C, 256, 0, s>>>(e.G, cs, N, m, rhs, d.gmode == 2 ? d.qp : d.np, d.gmode == 2 ? e.S : nullptr, e.tau2);
+  // operand maps of the ring-fed kernels: the chains' matrices stacked along the k axis (chain c, column k -> k-row
+  // c N + k), boxes as wide as a tile / a half / a quarter tile (+ 4 rows of padding); the stacked panel inverses
+  const CUtensorMap mG = make_map(e.G, N, (uint64_t)N * d.C, N, SY_LDS);
+  const CUtensorMap mG2 = make_map(e.G, N, (uint64_t)N * d.C, N, SY_BT / 2 + 4);
+  const CUtensorMap mG4 = make_map(e.G, N, (uint64_t)N * d.C, N, SY_BT / 4 + 4);
+  const CUtensorMap mL = make_map(e.Linv, PB, (uint64_t)PB * T * d.C, PB, SY_LDS);
+  auto mI = [&](int ns) -> const CUtensorMap& { return ns == 4 ? mG4 : (ns == 2 ? mG2 : mG); };
 
   if (!latency) {
     // ---- (A) ----
@@ -1527,20 +1583,20 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
           cudaEventRecord(fj.fork, s);
           cudaStreamWaitEvent(sideA, fj.fork, 0);
           dim3 g2(d.C, T - J - 1);
-          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, sideA>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J + 1, 1);
+          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, sideA>>>(mG, mG, 0, e.G, cs, N, m + 1, nk, J, J + 1, 1);
           cudaEventRecord(fj.join, sideA);
           dim3 g1(d.C, 1);
-          ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J, 1);
+          ++g_launches; k_chol_update<<<g1, SY_THREADS, SYRK_SMEM, s>>>(mG, mG, 0, e.G, cs, N, m + 1, nk, J, J, 1);
         } else {
           dim3 g2(d.C, T - J);
-          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, e.G, N, m + 1, nk, J, J, 1);
+          ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, s>>>(mG, mG, 0, e.G, cs, N, m + 1, nk, J, J, 1);
         }
       }
       ++g_launches; k_potf2_inv<<<d.C, 256, POTF2_SMEM, s>>>(e.G, cs, N, J, e.Linv, T, e.status, 0);
       if (fork) cudaStreamWaitEvent(s, fj.join, 0);
       if (J + 1 < T) {
         dim3 g1(d.C, T - J - 1);
-        ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(e.G, cs, N, m + 1, J, J + 1, e.Linv + (size_t)J * PB * PB, ls, 1);
+        ++g_launches; k_trsm_dmma<<<g1, SY_THREADS, SYRK_SMEM, s>>>(mL, mG, e.G, cs, N, m + 1, J, J + 1, 1);
       }
     }
     return;
@@ -1574,7 +1630,7 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
     else if (small_tiles && ns == 2)
       k_small_tile<2, 8><<<g, 256, small_tile_smem(64), st>>>(e.G, cs, N, J, ib_first, 2, Lj, ls, PB, J * PB, 0);
     else
-      k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM, st>>>(e.G, cs, N, m + 1, J, ib_first, Lj, ls, ns);
+      k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM, st>>>(mL, mI(ns), e.G, cs, N, m + 1, J, ib_first, ns);
   };
   // The late part of the diagonal tile (J+1, J+1) -- the contribution of panel J -- either runs inside k_potf2_inv
   // (one SM: ~12 us of DMMA) or, when the chains are few enough for 4-8 CTAs per tile, as its own strip kernel Ud(J)
@@ -1618,9 +1674,9 @@ void launch_cholesky(const Engine& e, double* rhs, const ForkJoin& fj, cudaStrea
       else if (small_tiles && ns2 == 2)
         k_small_tile<1, 8><<<g2, 256, small_tile_smem(64), side>>>(e.G, cs, N, J + 1, J + 2, 2, e.G + (size_t)J * PB * N + (size_t)(J + 1) * PB, cs, N, J * PB, 0);
       else
-        k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G + (size_t)J * PB * N, cs, N, e.G, N, m + 1, PB / SY_BK, J + 1, J + 2, ns2);
+        k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(mG, mI(ns2), J * PB, e.G, cs, N, m + 1, PB / SY_BK, J + 1, J + 2, ns2);
       if (fork) cudaEventRecord(evL[J], side);
-      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(e.G, cs, N, e.G, N, m + 1, (J + 1) * PB / SY_BK,
+      ++g_launches; k_chol_update<<<g2, SY_THREADS, SYRK_SMEM, side>>>(mG, mI(ns2), 0, e.G, cs, N, m + 1, (J + 1) * PB / SY_BK,
                                                                    J + 2, J + 2, ns2);
       if (fork) cudaEventRecord(evE[J], side);
     }

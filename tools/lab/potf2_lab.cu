@@ -86,17 +86,20 @@ int main(int argc, char** argv) {
     printf("    total                  %7.2f us\n", (st[17] - st[0]) * 1e-3);
 #endif
   }
+  const CUtensorMap mG1 = make_map(G, N, (uint64_t)N * C, N, SY_LDS), mG2 = make_map(G, N, (uint64_t)N * C, N, SY_BT / 2 + 4),
+                    mG4 = make_map(G, N, (uint64_t)N * C, N, SY_BT / 4 + 4), mL = make_map(Linv, PB, (uint64_t)PB * T * C, PB, SY_LDS);
   for (int ns = 1; ns <= 4; ns *= 2) {
+    const CUtensorMap& mI = ns == 4 ? mG4 : (ns == 2 ? mG2 : mG1);
     char nm[96];
     snprintf(nm, 96, "k_trsm_dmma 1 tile/chain, %d strips", ns);
-    timeit(nm, [&] { dim3 g(C, ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, N, 0, 1, Linv, (size_t)T * PB * PB, ns); });
+    timeit(nm, [&] { dim3 g(C, ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(mL, mI, G, cs, N, N, 0, 1, ns); });
     snprintf(nm, 96, "k_trsm_dmma T-2 tiles/chain, %d strips", ns);
-    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, N, 0, 2, Linv, (size_t)T * PB * PB, ns); });
+    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_trsm_dmma<<<g, SY_THREADS, SYRK_SMEM>>>(mL, mI, G, cs, N, N, 0, 2, ns); });
     snprintf(nm, 96, "k_chol_update depth 128, T-2 tiles, %d strips", ns);
-    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, G, N, N, 8, 1, 2, ns); });
+    timeit(nm, [&] { dim3 g(C, (T - 2) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(mG1, mI, 0, G, cs, N, N, 8, 1, 2, ns); });
     const int jb = 4 < T ? 4 : T - 1;
     snprintf(nm, 96, "k_chol_update depth 512, col %d incl diag, %d strips", jb, ns);
-    timeit(nm, [&] { dim3 g(C, (T - jb) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(G, cs, N, G, N, N, 32, jb, jb, ns); });
+    timeit(nm, [&] { dim3 g(C, (T - jb) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(mG1, mI, 0, G, cs, N, N, 32, jb, jb, ns); });
   }
   timeit("k_bwd_stream", [&] { k_bwd_stream<<<C, 256, bwd_smem(N)>>>(G, cs, N, N - 1, Linv, xout, N, nullptr, 0, bwd_stages(N)); });
   timeit("empty launch pair", [&] { k_augment<<<1, 256>>>(G, cs, N, 1, G0, N, nullptr, nullptr); });
