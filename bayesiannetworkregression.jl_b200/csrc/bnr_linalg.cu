@@ -1101,13 +1101,15 @@ __global__ void __launch_bounds__(256) k_small_tile(double* __restrict__ G, size
 
 // ------------------------------------------------------------------------------------------------------------
 // backward solve  L' x = b,  b = w (+ addz), w = row m of the factor (see above).  One CTA per chain streams the factor
-// once, bottom-right to top-left, in parts of BW_COLS columns x 128 rows through a multi-stage cp.async ring: every
-// thread issues 16-byte LDGSTS copies (a 1 KB column is one coalesced request of 64 threads).  The first version fed
-// the ring with 1 KB bulk copies from a producer warp; the TMA engine accepts only about one such request per 30 ns,
-// which capped the solve at ~30 GB/s per CTA (157 us for a 1024 x 1024 factor).  8 warps turn every part into BW_COLS
-// dot products (warp per BW_COLS / 8 columns, lanes over the rows):
+// once, bottom-right to top-left, in parts of BW_COLS columns x 128 rows through a ring of TMA tensor-map boxes (one
+// 32 KB request per part, full / empty mbarriers, a producer warp with one active lane).  History: 1 KB bulk copies from
+// a producer warp (the TMA engine accepts ~one request per 30 ns: 157 us for a 1024 x 1024 factor), then 16-byte
+// LDGSTS copies by all threads with a __syncthreads per part (118 us: ~500 of the ~1600 cycles per part were LDGSTS
+// issue, the rest the per-part barrier chain), now box loads and barriers only at block-column boundaries.
+// 8 consumer warps turn every part into BW_COLS dot products (warp per BW_COLS / 8 columns, lanes over the rows):
 //   off-diagonal block (I, J): b_J -= L[I, J]' x_I          diagonal block J: x_J = Linv_J' b_J
-// grid = C, block = 256.
+// Within a block column every warp owns its entries of b_J, so the consumers only meet before and after the diagonal
+// block.   grid = C, block = 288 (8 consumer warps + the producer warp).
 // ------------------------------------------------------------------------------------------------------------
 #ifndef BNR_BW_COLS
 #define BNR_BW_COLS 32
@@ -1117,77 +1119,76 @@ constexpr int BW_NH = PB / BW_COLS;              // parts per block
 constexpr int BW_CPW = BW_COLS / 8;              // columns per warp
 constexpr int BW_MAX_STAGES = 6;
 constexpr int BW_STAGE_DBL = BW_COLS * PB;
+constexpr int BW_THREADS = 288;
 static int bwd_stages(int N) {
-  const size_t budget = 227 * 1024 - sizeof(double) * (size_t)N - 256;
+  const size_t budget = 227 * 1024 - sizeof(double) * (size_t)N - 512;
   int ns = (int)(budget / (sizeof(double) * BW_STAGE_DBL));
   return ns > BW_MAX_STAGES ? BW_MAX_STAGES : ns;
 }
-static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 64; }
+static size_t bwd_smem(int N) { return sizeof(double) * ((size_t)bwd_stages(N) * BW_STAGE_DBL + N) + 256; }
 
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {      // wait until at most n groups are pending (n < 6)
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    default: cp_async_wait<4>(); break;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_bwd_stream(const double* __restrict__ G, size_t chain_stride, int N, int m,
-                                                    const double* __restrict__ Linv, double* __restrict__ out,
-                                                    int out_stride, const double* __restrict__ addz, int addz_stride,
-                                                    int nstages) {
-  extern __shared__ __align__(16) double sm[];
+// tmG: the chain-stacked factor {rows, columns x chains}, tmL: the stacked panel inverses {128, 128 x panels x chains};
+// boxes of 128 rows x BW_COLS columns (dense in shared memory: part[col * 128 + row])
+__global__ void __launch_bounds__(BW_THREADS) k_bwd_stream(const __grid_constant__ CUtensorMap tmG,
+                                                           const __grid_constant__ CUtensorMap tmL,
+                                                           const double* __restrict__ G, size_t chain_stride, int N, int m,
+                                                           double* __restrict__ out, int out_stride,
+                                                           const double* __restrict__ addz, int addz_stride, int nstages) {
+  extern __shared__ __align__(128) double sm[];
   double* ring = sm;
   double* x = sm + (size_t)nstages * BW_STAGE_DBL;     // [N] right-hand side, overwritten block by block by x
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(x + N);
+  unsigned long long* empty = full + BW_MAX_STAGES;
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = N / PB;
   const double* Gc = G + (size_t)c * chain_stride;
-  const double* Lc = Linv + (size_t)c * T * PB * PB;
   const int total = T * (T + 1) / 2 * BW_NH;
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
 
-  // producer state: the part that is issued next, in consumption order (J down, I from T-1 down to J, h up)
-  int pJ = T - 1, pI = T - 1, ph = 0, issued = 0;
-  auto issue = [&]() {
-    if (issued < total) {
-      double* dst = ring + (size_t)(issued % nstages) * BW_STAGE_DBL;
-      const bool dg = (pI == pJ);
-      const double* src = dg ? Lc + (size_t)pJ * PB * PB + (size_t)ph * BW_COLS * PB
-                             : Gc + (size_t)(pJ * PB + ph * BW_COLS) * N + (size_t)pI * PB;
-      const size_t cs = dg ? PB : N;
-      const int chunk = tid & 63, c0 = tid >> 6;
-#pragma unroll
-      for (int i = 0; i < BW_COLS / 4; ++i) {
-        const int col = c0 + 4 * i;
-        cp_async16(dst + col * PB + chunk * 2, src + (size_t)col * cs + chunk * 2);
+  if (warp == 8) {
+    // ---- producer: the parts in consumption order (J down, I from T-1 down to J, h up) ----
+    if (lane == 0) {
+      int pJ = T - 1, pI = T - 1, ph = 0;
+      for (int p = 0; p < total; ++p) {
+        const int stage = p % nstages;
+        mbar_wait(&empty[stage], ((p / nstages) & 1) ^ 1);
+        mbar_expect_tx(&full[stage], BW_STAGE_DBL * 8u);
+        double* dst = ring + (size_t)stage * BW_STAGE_DBL;
+        if (pI == pJ) tma_load_2d(dst, &tmL, 0, (c * T + pJ) * PB + ph * BW_COLS, &full[stage]);
+        else tma_load_2d(dst, &tmG, pI * PB, c * N + pJ * PB + ph * BW_COLS, &full[stage]);
+        if (++ph == BW_NH) { ph = 0; if (--pI < pJ) { --pJ; pI = T - 1; } }
       }
-      ++issued;
-      if (++ph == BW_NH) { ph = 0; if (--pI < pJ) { --pJ; pI = T - 1; } }
     }
-    cp_async_commit();                                 // (an empty group keeps the group count in step)
-  };
-  for (int s = 0; s < nstages - 1; ++s) issue();
-  for (int k = tid; k < N; k += blockDim.x)
+    return;
+  }
+
+  for (int k = tid; k < N; k += 256)
     x[k] = (k < m) ? Gc[(size_t)k * N + m] + (addz ? addz[(size_t)c * addz_stride + k] : 0.0) : 0.0;
+  named_bar_sync(1, 256);
 
   int it = 0;
-  double xn[BW_NH][BW_CPW];                          // diagonal-block results of this warp's columns (all parts)
   for (int J = T - 1; J >= 0; --J) {
     for (int I = T - 1; I >= J; --I) {
       const bool dg = (I == J);
+      if (dg) named_bar_sync(1, 256);                  // every warp's updates of b_J are in
+      const double* v = x + I * PB;
+      const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
+      double xn[BW_NH][BW_CPW];                        // diagonal block: this warp's entries of x_J
 #pragma unroll
       for (int h = 0; h < BW_NH; ++h, ++it) {
-        cp_async_wait_dyn(nstages - 2);              // this thread's copies of part `it` have landed
-        __syncthreads();                             // ... everybody's; part it-1 is consumed; b / x updates visible
-        issue();                                     // refill the buffer part it-1 occupied
-        const double* v = x + I * PB;
-        const double v0 = v[lane], v1 = v[lane + 32], v2 = v[lane + 64], v3 = v[lane + 96];
-        const double* B = ring + (size_t)(it % nstages) * BW_STAGE_DBL + (size_t)(warp * BW_CPW) * PB + lane;
+        const int stage = it % nstages;
+        mbar_wait(&full[stage], (it / nstages) & 1);
+        const double* B = ring + (size_t)stage * BW_STAGE_DBL + (size_t)(warp * BW_CPW) * PB + lane;
         double acc[BW_CPW];
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q)
           acc[q] = B[q * PB] * v0 + B[q * PB + 32] * v1 + B[q * PB + 64] * v2 + B[q * PB + 96] * v3;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);     // this warp is done with the part
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q) {
 #pragma unroll
@@ -1202,17 +1203,18 @@ __global__ void __launch_bounds__(256) k_bwd_stream(const double* __restrict__ G
           for (int q = 0; q < BW_CPW; ++q) bj[q] -= acc[q];
         }
       }
-    }
-    __syncthreads();                                 // everybody has read b_J
-    if (lane == 0) {
+      if (dg) {
+        named_bar_sync(1, 256);                        // everybody has read b_J
+        if (lane == 0) {
 #pragma unroll
-      for (int h = 0; h < BW_NH; ++h)
+          for (int h = 0; h < BW_NH; ++h)
 #pragma unroll
-        for (int q = 0; q < BW_CPW; ++q) x[J * PB + h * BW_COLS + warp * BW_CPW + q] = xn[h][q];
+            for (int q = 0; q < BW_CPW; ++q) x[J * PB + h * BW_COLS + warp * BW_CPW + q] = xn[h][q];
+        }
+        named_bar_sync(1, 256);                        // x_J is visible
+      }
     }
-    // (x_J becomes visible to the other warps at the __syncthreads of the next part)
   }
-  __syncthreads();
   for (int k = tid; k < N; k += 256) out[(size_t)c * out_stride + k] = x[k];
 }
 
@@ -1414,12 +1416,13 @@ bool tmap_setup() {
   return true;
 }
 // rows beyond `rows` (the box is 4 rows wider than a tile) and k-rows beyond `krows` read as zeros
-static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows) {
+static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows,
+                            uint32_t box_k = SY_BK) {
   CUtensorMap m;
   memset(&m, 0, sizeof(m));
   const cuuint64_t dims[2] = {rows, krows};
   const cuuint64_t strides[1] = {ld * sizeof(double)};
-  const cuuint32_t box[2] = {box_rows, (cuuint32_t)SY_BK};
+  const cuuint32_t box[2] = {box_rows, box_k};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = (tmap_setup() ? g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -1428,7 +1431,7 @@ static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, u
   if (r != CUDA_SUCCESS) {
     // (bnr_create has already checked tmap_setup(); a failure here is a programming error of the caller's geometry)
     fprintf(stderr, "[bnr] cuTensorMapEncodeTiled failed (%d) for a %llu x %llu operand, box %u x %d\n", (int)r,
-            (unsigned long long)rows, (unsigned long long)krows, box_rows, SY_BK);
+            (unsigned long long)rows, (unsigned long long)krows, box_rows, (int)box_k);
     abort();
   }
   return m;
@@ -1689,8 +1692,10 @@ void launch_chol_solve(const Engine& e, double* out, const double* addz, cudaStr
   const int N = d.gdim;
   const int m = d.gmode == 2 ? d.q : d.n;
   const int stride = d.gmode == 2 ? d.qp : d.np;
-  ++g_launches; k_bwd_stream<<<d.C, 256, bwd_smem(N), s>>>(e.G, (size_t)N * N, N, m, e.Linv, out, stride, addz, stride,
-                                                        bwd_stages(N));
+  const CUtensorMap tmG = make_map(e.G, N, (uint64_t)N * d.C, N, PB, BW_COLS);
+  const CUtensorMap tmL = make_map(e.Linv, PB, (uint64_t)PB * (N / PB) * d.C, PB, PB, BW_COLS);
+  ++g_launches; k_bwd_stream<<<d.C, BW_THREADS, bwd_smem(N), s>>>(tmG, tmL, e.G, (size_t)N * N, N, m, out, stride, addz, stride,
+                                                               bwd_stages(N));
 }
 
 int chol_max_dim() { return CHOL_MAX_DIM; }

@@ -101,7 +101,8 @@ int main(int argc, char** argv) {
     snprintf(nm, 96, "k_chol_update depth 512, col %d incl diag, %d strips", jb, ns);
     timeit(nm, [&] { dim3 g(C, (T - jb) * ns); k_chol_update<<<g, SY_THREADS, SYRK_SMEM>>>(mG1, mI, 0, G, cs, N, N, 32, jb, jb, ns); });
   }
-  timeit("k_bwd_stream", [&] { k_bwd_stream<<<C, 256, bwd_smem(N)>>>(G, cs, N, N - 1, Linv, xout, N, nullptr, 0, bwd_stages(N)); });
+  const CUtensorMap bG = make_map(G, N, (uint64_t)N * C, N, PB, BW_COLS), bL = make_map(Linv, PB, (uint64_t)PB * T * C, PB, PB, BW_COLS);
+  timeit("k_bwd_stream", [&] { k_bwd_stream<<<C, BW_THREADS, bwd_smem(N)>>>(bG, bL, G, cs, N, N - 1, xout, N, nullptr, 0, bwd_stages(N)); });
   timeit("empty launch pair", [&] { k_augment<<<1, 256>>>(G, cs, N, 1, G0, N, nullptr, nullptr); });
   return 0;
 }
