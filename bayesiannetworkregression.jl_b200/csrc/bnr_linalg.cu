@@ -1296,6 +1296,10 @@ __global__ void __launch_bounds__(256) k_xmma(const double* __restrict__ X, int 
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  // chain fragments of this warp that hold a real chain: with few chains (a chain group of 2-3, config 4's 8) the 64-chain
+  // tile is mostly padding, and its DMMAs -- not the stream of X -- bounded the kernel (2 us per k-step for 16 KB)
+  int nfv = (N - n0 - wn * 32 + 7) >> 3;
+  nfv = nfv < 0 ? 0 : (nfv > 4 ? 4 : nfv);
 
   for (int s = 0; s < XM_STAGES - 1; ++s) {
     if (s < nsteps) load_stage(s);
@@ -1308,6 +1312,7 @@ __global__ void __launch_bounds__(256) k_xmma(const double* __restrict__ X, int 
     cp_async_commit();
     const double* As = sm + (size_t)(step % XM_STAGES) * XM_STAGE_DBL;
     const double* Vs = As + XM_A_DBL;
+    if (nfv == 0) continue;                          // (a warp without a real chain only keeps the barriers company)
 #pragma unroll
     for (int k4 = 0; k4 < XM_BK / 4; ++k4) {
       const int kr = k4 * 4 + lk;
@@ -1316,11 +1321,14 @@ __global__ void __launch_bounds__(256) k_xmma(const double* __restrict__ X, int 
       for (int mf = 0; mf < 4; ++mf)
         af[mf] = (TRANS == 0) ? As[kr * XM_LDM + wm * 32 + mf * 8 + lr] : As[(wm * 32 + mf * 8 + lr) * XM_LDK + kr];
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) bf[nf] = Vs[(wn * 32 + nf * 8 + lr) * XM_LDK + kr];
+      for (int nf = 0; nf < 4; ++nf) bf[nf] = (nf < nfv) ? Vs[(wn * 32 + nf * 8 + lr) * XM_LDK + kr] : 0.0;
 #pragma unroll
-      for (int mf = 0; mf < 4; ++mf)
+      for (int nf = 0; nf < 4; ++nf) {
+        if (nf < nfv) {
 #pragma unroll
-        for (int nf = 0; nf < 4; ++nf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+          for (int mf = 0; mf < 4; ++mf) dmma884(acc[mf][nf][0], acc[mf][nf][1], af[mf], bf[nf]);
+        }
+      }
     }
   }
   cp_async_wait<0>();
