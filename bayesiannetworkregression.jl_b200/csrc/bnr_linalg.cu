@@ -90,7 +90,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // NOTE the ring is written by the TMA engine behind the compiler's back: the consumer-side pointers into it must NOT
 // be __restrict__ (with a compile-time trip count the compiler then reuses the fragments of a stage's previous
 // occupant); the "memory" clobber of mbar_wait is what orders the fragment loads after the hand-shake.
-// grid = (C, tiles), block = 384 (2 consumer warpgroups + 1 producer warpgroup, registers re-balanced with
+// grid = (C, k-splits, tiles), block = 384 (2 consumer warpgroups + 1 producer warpgroup, registers re-balanced with
 // setmaxnreg: 232 per consumer thread, 40 per producer thread); dynamic smem = SYRK_SMEM.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SY_BT = 128;        // tile edge
@@ -313,7 +313,7 @@ template <int MODE>
 __device__ __forceinline__ void
 syrk_body(const CUtensorMap* tmj, const CUtensorMap* tmi, int jy0, int iy0, const double* __restrict__ scale,
           size_t scale_stride, double* __restrict__ Cm, size_t c_chain_stride, int np, int nvalid, int nk, int origin,
-          double diag_add, int part = 0, int nstrip = 1) {
+          double diag_add, int part = 0, int nstrip = 1, int tile_index = 0) {
   extern __shared__ __align__(128) double smem[];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)SY_STAGES * SY_STAGE_DBL);
   unsigned long long* empty = full + SY_STAGES;
@@ -321,21 +321,27 @@ syrk_body(const CUtensorMap* tmj, const CUtensorMap* tmi, int jy0, int iy0, cons
   const int c = blockIdx.x;          // chains vary fastest: the 64 CTAs that share one X tile run back to back (L2 reuse)
   int ib, jb;
   if (MODE == 0) {
-    // blockIdx.y enumerates the lower-triangular tiles, the strictly-lower (full-cost) ones first and the
-    // diagonal (half-cost) ones last, so the tail of the grid is made of cheap CTAs
-    const int T = np / SY_BT, noff = T * (T - 1) / 2;
+    // tile_index enumerates the lower-triangular tiles by decreasing cost, so that the tail of the grid is made of
+    // cheap CTAs: the strictly-lower (full-cost) tiles, the diagonal (half-cost) ones, and last the strictly-lower
+    // tiles of a SHORT last row block (<= 32 valid rows: a quarter of the DMMAs)
+    const int T = np / SY_BT;
+    const bool short_last = T > 1 && nvalid - (T - 1) * SY_BT <= 32;
+    const int noff = short_last ? (T - 1) * (T - 2) / 2 : T * (T - 1) / 2;
 #ifdef SYRK_LAB_ONLY_DIAG
-    const int t = blockIdx.y + noff;
+    const int t = tile_index + noff;
 #else
-    const int t = blockIdx.y;
+    const int t = tile_index;
 #endif
     if (t < noff) {
       ib = (int)((1.0 + sqrt(1.0 + 8.0 * t)) * 0.5);
       while (ib * (ib - 1) / 2 > t) --ib;
       while ((ib + 1) * ib / 2 <= t) ++ib;
       jb = t - ib * (ib - 1) / 2;
-    } else {
+    } else if (t < noff + T) {
       ib = jb = t - noff;
+    } else {
+      ib = T - 1;
+      jb = t - noff - T;
     }
   } else {
     // MODE 1 (Cholesky update of block column jb = origin) and MODE 2 (panel solve of block column jb): the CTAs of a
@@ -345,9 +351,9 @@ syrk_body(const CUtensorMap* tmj, const CUtensorMap* tmi, int jy0, int iy0, cons
     // (bit-identical results), a quarter of the DMMA chain per CTA.  A diagonal tile is then computed like any other
     // (its upper triangle is written too; nobody reads it).
     jb = origin;
-    ib = part + (int)blockIdx.y / nstrip;
+    ib = part + tile_index / nstrip;
   }
-  const int strip = (MODE == 0) ? 0 : (int)blockIdx.y % nstrip;
+  const int strip = (MODE == 0) ? 0 : tile_index % nstrip;
   const int rows_i = SY_BT / nstrip;
   const int i0 = ib * SY_BT + strip * rows_i, j0 = jb * SY_BT;
   const bool diag = (ib == jb) && nstrip == 1;
@@ -439,14 +445,18 @@ __global__ void __launch_bounds__(SY_THREADS, 1)
 k_gram_syrk(const __grid_constant__ CUtensorMap tmX, const double* __restrict__ scale, size_t scale_stride,
             double* __restrict__ G, size_t g_chain_stride, int np, int nvalid, int nk, double diag_add,
             int nk_split, double* __restrict__ ws, int ws_cap) {
-  const int z = blockIdx.z;
+  // grid = (chains, k-splits, tiles): the hardware hands out CTAs x-fastest, z-slowest, so all splits of the expensive
+  // tiles start before any cheap tile (with the split as the slowest index the last split's full-cost tiles started
+  // last and the grid ended in a ~340 us tail of a few busy SMs)
+  const int z = blockIdx.y, t = blockIdx.z;
   if (z == 0) {
-    syrk_body<0>(&tmX, &tmX, 0, 0, scale, scale_stride, G, g_chain_stride, np, nvalid, nk < nk_split ? nk : nk_split, 0, diag_add);
+    syrk_body<0>(&tmX, &tmX, 0, 0, scale, scale_stride, G, g_chain_stride, np, nvalid, nk < nk_split ? nk : nk_split, 0, diag_add,
+                 0, 1, t);
   } else {
     const int kt0 = z * nk_split;
     const int nkl = (nk - kt0) < nk_split ? (nk - kt0) : nk_split;
     syrk_body<0>(&tmX, &tmX, kt0 * SY_BK, kt0 * SY_BK, scale + (size_t)kt0 * SY_BK, scale_stride,
-                 ws + (size_t)(z - 1) * g_chain_stride, (size_t)ws_cap * g_chain_stride, np, nvalid, nkl, 0, 0.0);
+                 ws + (size_t)(z - 1) * g_chain_stride, (size_t)ws_cap * g_chain_stride, np, nvalid, nkl, 0, 0.0, 0, 1, t);
   }
 }
 
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1)
 k_chol_update(const __grid_constant__ CUtensorMap tmJ, const __grid_constant__ CUtensorMap tmI, int kcol0,
               double* __restrict__ G, size_t chain_stride, int np, int nvalid, int nk, int jb, int ib_first, int nstrip) {
   const int y0 = (int)blockIdx.x * np + kcol0;
-  syrk_body<1>(&tmJ, &tmI, y0, y0, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, ib_first, nstrip);
+  syrk_body<1>(&tmJ, &tmI, y0, y0, nullptr, 0, G, chain_stride, np, nvalid, nk, jb, 0.0, ib_first, nstrip, (int)blockIdx.y);
 }
 
 // panel solve on the tensor cores: G[I, J] <- G[I, J] Linv_J' for the row blocks I = ib_first, ... (in place: a CTA
@@ -488,7 +498,7 @@ k_trsm_dmma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUt
             size_t chain_stride, int np, int nvalid, int jb, int ib_first, int nstrip) {
   const int T = np / SY_BT;
   syrk_body<2>(&tmL, &tmI, ((int)blockIdx.x * T + jb) * SY_BT, (int)blockIdx.x * np + jb * SY_BT, nullptr, 0, G, chain_stride,
-               np, nvalid, SY_BT / SY_BK, jb, 0.0, ib_first, nstrip);
+               np, nvalid, SY_BT / SY_BK, jb, 0.0, ib_first, nstrip, (int)blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1467,11 +1477,11 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
   const int ns = e.syrk_ws ? e.syrk_ws_cap + 1 : 1;   // fixed per handle: chain groups must not change the summation order
   const int nk_split = (nk + ns - 1) / ns;
 #if defined(SYRK_LAB_ONLY_DIAG)
-  dim3 grid(d.C, T, ns);
+  dim3 grid(d.C, ns, T);
 #elif defined(SYRK_LAB_ONLY_OFFDIAG)
-  dim3 grid(d.C, T * (T - 1) / 2, ns);
+  dim3 grid(d.C, ns, T * (T - 1) / 2);
 #else
-  dim3 grid(d.C, T * (T + 1) / 2, ns);
+  dim3 grid(d.C, ns, T * (T + 1) / 2);
 #endif
   const size_t gs = (size_t)d.np * d.np;
   const CUtensorMap tmX = make_map(e.X, d.np, d.qp, d.np, SY_LDS);
@@ -1494,7 +1504,7 @@ void launch_syrk_G(const Engine& e, cudaStream_t s) {
 // XtX (lower tiles of a qp x qp column-major matrix) from XT[i * qp + j] = X(i, j) (np rows, zero padded)
 void launch_xtx(const Dims& d, const double* XT, const double* ones, double* XtX, cudaStream_t s) {
   const int T = d.qp / SY_BT;
-  dim3 grid(1, T * (T + 1) / 2);
+  dim3 grid(1, 1, T * (T + 1) / 2);
   const CUtensorMap tmXT = make_map(XT, d.qp, d.np, d.qp, SY_LDS);
   ++g_launches; k_gram_syrk<<<grid, SY_THREADS, SYRK_SMEM, s>>>(tmXT, ones, 0, XtX, 0, d.qp, d.q, d.np / SY_BK, 0.0,
                                                             d.np / SY_BK, nullptr, 0);
