@@ -1197,8 +1197,6 @@ __global__ void __launch_bounds__(BW_THREADS) k_bwd_stream(const __grid_constant
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q)
           acc[q] = B[q * PB] * v0 + B[q * PB + 32] * v1 + B[q * PB + 64] * v2 + B[q * PB + 96] * v3;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);     // this warp is done with the part
 #pragma unroll
         for (int q = 0; q < BW_CPW; ++q) {
 #pragma unroll
@@ -1212,6 +1210,13 @@ __global__ void __launch_bounds__(BW_THREADS) k_bwd_stream(const __grid_constant
 #pragma unroll
           for (int q = 0; q < BW_CPW; ++q) bj[q] -= acc[q];
         }
+        // Release the part only HERE, after the shuffles (and the update of b_J) have consumed every lane's loads.
+        // An arrive right after the loads were ISSUED is not enough: it is not ordered behind shared-memory loads
+        // that still wait in the memory pipe, the producer's next box then overwrote data that had not been read yet
+        // -- chains differed from run to run under load (tools/determinism_check.py found it; the SASS showed the
+        // DFMAs that consume the loads scheduled after the SYNCS.ARRIVE).
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
       }
       if (dg) {
         named_bar_sync(1, 256);                        // everybody has read b_J

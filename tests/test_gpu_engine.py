@@ -474,6 +474,31 @@ def test_full_size_runs_are_bitwise_reproducible_across_chain_groups(bnr, shape)
                     np.testing.assert_array_equal(np.asarray(st[c][k]), np.asarray(ref[c][k]), err_msg="%s chain %d groups %d" % (k, c, groups))
 
 
+def test_chains_are_reproducible_under_load(bnr):
+    """Three chain groups of config-3-sized problems keep every SM busy, so the producer/consumer rings run under memory
+    pressure: 24 chains x 40 sweeps, twice with the default grouping and once as a single group, must agree bit for bit.
+    (This is the check that caught a ring stage released before its shared-memory loads had been consumed: 1 in ~400
+    chain-sweeps was perturbed, invisible to the 5-sweep test above.)"""
+    V, R, n, C, K = 100, 7, 1000, 24, 40
+    rng = np.random.default_rng(31)
+    q = V * (V + 1) // 2
+    X = rng.normal(size=(n, q)) * (rng.random((n, q)) < 0.6)
+    y = 10 + X[:, :15].sum(axis=1) + rng.normal(0, 3, size=n)
+    ref = None
+    for groups in (0, 0, 1):
+        with bnr.Engine(X, y, R, num_chains=C, seed=7, chain_groups=groups) as eng:
+            eng.init_state()
+            eng.run(K)
+            st = np.stack([np.concatenate([np.ravel(eng.get_state(c, k)) for k in ("gamma", "S", "u", "tau2", "M", "lam")])
+                           for c in range(C)])
+            assert not (eng.status() & ~1).any()
+        if ref is None:
+            ref = st
+        else:
+            differ = [c for c in range(C) if not np.array_equal(ref[c], st[c])]
+            assert not differ, "chains %s differ from the first run (chain_groups=%d)" % (differ, groups)
+
+
 def test_config1_shipped_example(bnr, golden):
     """BASELINE config 1: Fit! on the shipped example (examples/matrix_networks.csv: n=100, V=30, q=465), R=5.
     The reference's own stored 50 000-iteration fit of this data (older diagonal-free model, R=7;
