@@ -1,8 +1,8 @@
 // Dense FP64 linear algebra of the gamma draw (update_gamma!, src/gibbs.jl:420-438), batched over chains:
-//   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, TMA bulk-copy ring + mbarriers
+//   G_c = X diag(S_c) X' + I          -> k_gram_syrk : FP64 tensor-core (DMMA m8n8k4) SYRK, ring of TMA tensor-map boxes + mbarriers
 //   G_c = L_c L_c', w = L_c^-1 rhs    -> blocked left-looking Cholesky: k_augment / k_chol_update (DMMA) / k_potf2_inv /
-//                                        k_trsm_dmma (DMMA); the forward solve rides along as a bordering row
-//   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a TMA ring)
+//                                        k_trsm_dmma (DMMA) / k_small_tile; the forward solve rides along as a bordering row
+//   a4  = L_c^-T w                    -> k_bwd_stream (the factor streamed once through a ring of TMA boxes)
 //   X v, X' a4 (all chains at once)   -> k_xmma (tall-skinny DMMA GEMM, deterministic split-K)
 // tcgen05 has no FP64 kind, so the Blackwell tensor path for this contraction is the warp-level DMMA.
 #include <cstdio>
@@ -76,9 +76,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 //   MODE 2:  C_c[i][j]  = sum_{k < 128} C_c[i][k] Linv_c[j][k]       panel solve with the inverted diagonal block
 // The operand is "k-major": element (row, k) at A[row + ld*k] (rows contiguous) - exactly how X (column-major
 // n x q) and a column panel of the column-major G are stored, so a 128-row x 16-k tile is sixteen contiguous
-// 1 KB rows.  A dedicated producer warp streams them into a 4-stage shared-memory ring with TMA-engine bulk
-// copies (cp.async.bulk, completion on "full" mbarriers); the 8 consumer warps never execute a block-wide
-// barrier in the main loop - they wait on "full", issue DMMA m8n8k4, and release the stage on "empty".
+// 1 KB rows = one box of a 2-D tensor map {rows, k}.  A dedicated producer warp loads one box per operand and stage
+// into a 4-stage shared-memory ring (cp.async.bulk.tensor.2d, completion on "full" mbarriers); the 8 consumer warps
+// never execute a block-wide barrier in the main loop - they wait on "full", issue DMMA m8n8k4, and release the
+// stage on "empty".
 // CTA tile 128 x 128, k-step 16.  The MMA "M" dimension runs along j (columns of C) and "N" along i (rows of C), so
 // every accumulator pair is two consecutive rows of one column of the column-major C -> 16-byte stores.  Strictly
 // lower tiles use a column-strip warp layout (syrk_strip_tile: 2 column fragments x all row fragments per warp),
@@ -86,7 +87,8 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // padded to 132 doubles (== 4 mod 16) which makes the (row, k) fragment loads bank-conflict free.
 // The per-chain scale s_c[k] is applied to the operand with the fewest fragments per warp (2): DMUL shares the
 // FP64 pipe with DMMA.  Work that cannot contribute is skipped: the symmetric half of diagonal tiles and row
-// fragments that lie entirely in the zero padding beyond n.
+// fragments that lie entirely in the zero padding beyond n.  The boxes are 132 rows wide (4 more than the tile):
+// the box pitch is the padded row stride, at the price of 3 % more L2 traffic.
 // NOTE the ring is written by the TMA engine behind the compiler's back: the consumer-side pointers into it must NOT
 // be __restrict__ (with a compile-time trip count the compiler then reuses the fragments of a stage's previous
 // occupant); the "memory" clobber of mbar_wait is what orders the fragment loads after the hand-shake.
@@ -511,14 +513,13 @@ k_trsm_dmma(const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUt
 //     the last row block.  (The corner entry sqrt(d - |w|^2) is never used.)
 //   * for J = 0 .. T-1:
 //       k_chol_update (DMMA): G[J.., J] -= L[J.., 0:J] L[J, 0:J]'
-//       k_potf2_inv   one CTA per chain: the 128 x 128 diagonal block arrives column-major through the TMA engine,
-//                     is factored in shared memory (32-wide steps: one warp factors 32 x 32 in registers with
-//                     shuffles, a thread per row eliminates below, everybody updates the trailing part in 2 x 2
-//                     register tiles), goes back with bulk stores, and is then INVERTED in place (32 x 32 diagonal
-//                     inverses by substitution, off-diagonal blocks by the recursive 2 x 2 block formula) -> Linv[c][J]
+//       k_potf2_inv   one CTA per chain: the 128 x 128 diagonal block is factored in shared memory in 32-wide steps,
+//                     software-pipelined around the pivot chain (one warp factors 32 x 32 in registers and publishes
+//                     its columns; the rows below, the diagonal-block inverses, the trailing updates, the bordered
+//                     inverse and the stores all run next to it, see the kernel) -> factor in place, Linv[c][J]
 //       k_trsm_dmma   (DMMA): G[I, J] <- G[I, J] Linv_J' for I > J -- the panel solve is a GEMM
-//   * backward solve L' x = w (+ z): k_bwd_stream, one CTA per chain streams the factor once (bulk copies into a
-//     shared-memory ring, 64-column half blocks), every step is a block mat-vec; the diagonal blocks use Linv.
+//   * backward solve L' x = w (+ z): k_bwd_stream, one CTA per chain streams the factor once (tensor-map boxes of
+//     128 rows x 32 columns into a shared-memory ring), every step is a block mat-vec; the diagonal blocks use Linv.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int PB = 128;            // panel / diagonal block size
 constexpr int CHOL_MAX_DIM = 8192; // largest factored dimension (the back solve keeps the solution vector in shared memory)
