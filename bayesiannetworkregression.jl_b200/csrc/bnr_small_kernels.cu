@@ -387,7 +387,10 @@ __global__ void __launch_bounds__(256) k_rhs(Engine e) {
 // flags: 1 = finish gamma, 2 = draw S, 4 = finish gamma in the q-form (gamma = W + beta, beta in e.t).
 // grid = (nparts, C), block = PART_BLOCK.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PART_BLOCK) k_gamma_gig(Engine e, int flags) {
+// (3 blocks per SM: the rejection samplers are chains of dependent FP64 transcendental sequences, so the kernel is bound by
+//  how many warps an SM can interleave -- 105 registers allowed 16 warps, 79 allow 24: config 4 1.404 -> 1.380 ms; 64
+//  registers would spill)
+__global__ void __launch_bounds__(PART_BLOCK, 3) k_gamma_gig(Engine e, int flags) {
   extern __shared__ double sm[];
   const Dims& d = e.d;
   const int c = blockIdx.y, tid = threadIdx.x, R = d.R;
