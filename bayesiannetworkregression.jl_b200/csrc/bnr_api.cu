@@ -54,8 +54,10 @@ struct ChainGroup {
   Engine e;                      // view of the handle's arrays restricted to chains [c0, c0 + e.d.C)
   int c0 = 0;
   cudaStream_t stream = nullptr;
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
+  // two-sweep graphs, one per parity of the u double buffer (index 1: e.u currently points at the second buffer), so an
+  // eager sweep -- an odd sweep count -- does not throw the captured graphs away
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
   cudaEvent_t done = nullptr;
   ForkJoin fj;                   // side stream of the Cholesky (off-diagonal panel updates)
   double* ws = nullptr;          // split-K workspace of this group
@@ -114,7 +116,8 @@ struct bnr_handle {
   cudaStream_t stream = nullptr;
   ChainGroup groups[MAX_GROUPS];
   int n_groups = 0;
-  bool graphs_ready = false;
+  bool graphs_ready[2] = {false, false};
+  const double* u_first = nullptr;   // e.u at creation: the parity of the double buffer is (e.u != u_first)
   cudaEvent_t ev_fork = nullptr;
   ForkJoin fj;                   // side stream for eager sweeps on the whole chain set
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -325,6 +328,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   e.edge_lk = dlk;
 
   DA(e.tau2, C); DA(e.u, C * d.V * d.R); DA(e.u_alt, C * d.V * d.R); DA(e.xi, C * d.V);
+  h->u_first = e.u;
   DA(e.gamma, C * d.qp); DA(e.S, C * d.qp); DA(e.theta, C); DA(e.Delta, C); DA(e.M, C * d.R * d.R);
   DA(e.mu, C); DA(e.lambda, C * d.R); DA(e.pi, C * 3 * d.R);
   DA(e.W, C * d.qp); DA(e.v, C * d.qp); DA(e.t, C * d.qp);
@@ -521,10 +525,12 @@ extern "C" int bnr_destroy(bnr_handle* h) {
 static void drop_graph(bnr_handle* h) {
   for (int g = 0; g < h->n_groups; ++g) {
     ChainGroup& G = h->groups[g];
-    if (G.gexec) { cudaGraphExecDestroy(G.gexec); G.gexec = nullptr; }
-    if (G.graph) { cudaGraphDestroy(G.graph); G.graph = nullptr; }
+    for (int par = 0; par < 2; ++par) {
+      if (G.gexec[par]) { cudaGraphExecDestroy(G.gexec[par]); G.gexec[par] = nullptr; }
+      if (G.graph[par]) { cudaGraphDestroy(G.graph[par]); G.graph[par] = nullptr; }
+    }
   }
-  h->graphs_ready = false;
+  h->graphs_ready[0] = h->graphs_ready[1] = false;
 }
 
 // X * gamma for the current state (cache used by tau2 and mu)
@@ -632,7 +638,8 @@ static Engine group_view(const bnr_handle* h, int c0, int Cg, long long* counter
 // The u double buffer flips every sweep, so every group's graph holds TWO sweeps; odd counts run one sweep eagerly
 // on the whole chain set.
 static int build_graphs(bnr_handle* h) {
-  if (h->graphs_ready) return BNR_OK;
+  const int par = (h->e.u != h->u_first) ? 1 : 0;
+  if (h->graphs_ready[par]) return BNR_OK;
   const double t0 = wall_ms();
   const long long before = g_launches;
   const int C = h->e.d.C, ng = h->n_groups;
@@ -645,12 +652,12 @@ static int build_graphs(bnr_handle* h) {
     CK(cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal));
     enqueue_sweep(e, G.ws, G.fj, G.stream);
     enqueue_sweep(e, G.ws, G.fj, G.stream);
-    CK(cudaStreamEndCapture(G.stream, &G.graph));
+    CK(cudaStreamEndCapture(G.stream, &G.graph[par]));
     // node priorities = priorities of the streams the kernels were captured from (main: greatest, side: least)
-    CK(cudaGraphInstantiate(&G.gexec, G.graph, getenv("BNR_NO_PRIO") ? 0 : cudaGraphInstantiateFlagUseNodePriority));
+    CK(cudaGraphInstantiate(&G.gexec[par], G.graph[par], getenv("BNR_NO_PRIO") ? 0 : cudaGraphInstantiateFlagUseNodePriority));
   }
   h->graph_kernels = g_launches - before;
-  h->graphs_ready = true;
+  h->graphs_ready[par] = true;
   if (g_timing) fprintf(stderr, "[bnr] graph capture + instantiate (%d groups, %lld kernels) %.2f ms\n", ng, h->graph_kernels, wall_ms() - t0);
   return BNR_OK;
 }
@@ -681,6 +688,7 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
   if (h->e.inj == nullptr && !h->aux_on && left >= 2) {
     int r = build_graphs(h);
     if (r) return r;
+    const int par = (h->e.u != h->u_first) ? 1 : 0;
     // fork: every group starts from the handle's counters and runs its sweeps without ever meeting the others
     CK(cudaEventRecord(h->ev_fork, h->stream));
     for (int g = 0; g < h->n_groups; ++g) {
@@ -690,7 +698,7 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
       CK(cudaMemcpyAsync(G.counters + 1, h->e.trace_row, sizeof(long long), cudaMemcpyDeviceToDevice, G.stream));
     }
     for (; left >= 2; left -= 2) {
-      for (int g = 0; g < h->n_groups; ++g) CK(cudaGraphLaunch(h->groups[g].gexec, h->groups[g].stream));
+      for (int g = 0; g < h->n_groups; ++g) CK(cudaGraphLaunch(h->groups[g].gexec[par], h->groups[g].stream));
       h->launches += h->graph_kernels;
     }
     // join
@@ -702,12 +710,18 @@ extern "C" int bnr_run(bnr_handle* h, int64_t n_iters) {
     CK(cudaMemcpyAsync(h->e.trace_row, h->groups[0].counters + 1, sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
   }
   for (; left > 0; --left) {
-    drop_graph(h);   // an eager sweep flips the u buffers relative to the captured graphs
+    // (an eager sweep flips the u buffers: the next graph run uses the graphs of the other parity)
     const long long before = g_launches;
     enqueue_sweep(h->e, h->ws, h->fj, h->stream);
     h->launches += g_launches - before;
   }
   CK(cudaEventRecord(h->ev1, h->stream));
+  // an odd count left the double buffer on the other parity: capture that parity's graphs now, while the device is
+  // still busy with what was just enqueued, instead of at the start of the next run
+  if (h->e.inj == nullptr && !h->aux_on && (h->graphs_ready[0] || h->graphs_ready[1])) {
+    int r = build_graphs(h);
+    if (r) return r;
+  }
   CK(cudaGetLastError());
   h->ran = true;
   return BNR_OK;

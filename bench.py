@@ -411,9 +411,12 @@ def main():
     # Summary reduced on the device, D2H of chain 1's gamma / xi table, the R-hat vectors and the Summary statistics.
     nsamp_e = min(max(2, K // 2), K)
     nburn_e = K + 1 - nsamp_e                      # nburn + nsamples rows = prior row + K sweeps
-    # one untimed 8-sweep Fit first: the steady state of the API is what is measured, not the first call's lazy loading
-    # of the Fit-only kernels (Summary select, R-hat) and, across ranks, NCCL's first all-gather
-    bnr.Fit(X, y, R, nburn=5, nsamples=4, num_chains=chains, seed=7, x_transform=False, filename=None,
+    # one untimed Fit first: the steady state of the API is what is measured, not the first call's lazy loading of the
+    # Fit-only kernels (Summary select, R-hat), across ranks NCCL's first all-gather, and the device allocator (a Fit of
+    # the same shape leaves every buffer of the timed one in libbnr's cache; a cudaMalloc of a new size was seen to take
+    # anything from 0.1 to 30 ms).  Same shape up to 256 sweeps, an 8-sweep one beyond.
+    wb, wn = (nburn_e, nsamp_e) if K <= 256 else (5, 4)
+    bnr.Fit(X, y, R, nburn=wb, nsamples=wn, num_chains=chains, seed=7, x_transform=False, filename=None,
             psrf_cutoff=float("inf"), device=local_rank, return_state="gamma_xi")
     barrier()
     t0 = time.perf_counter()
@@ -521,7 +524,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "chain-iterations/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "includes": "Fit(X, y, R; ...) + Summary through the public API (one bnr_fit call): handle creation "
-                    "(device buffers come from libbnr's cache, warmed by an untimed 8-sweep Fit), H2D of X,y from host memory, "
+                    "(device buffers come from libbnr's cache, warmed by one untimed Fit of the same shape), H2D of X,y from host memory, "
                     "graph capture, prior init, K sweeps, streamed R-hat (NCCL all-gather of the moments across ranks), "
                     "device Summary, D2H of chain-1 gamma/xi table, handle teardown"},
             "gpu_launches": int(launches),
