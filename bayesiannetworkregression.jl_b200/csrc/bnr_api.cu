@@ -459,6 +459,7 @@ static int create_impl(bnr_handle* h, const bnr_params* p, const double* X, cons
   e.inj = nullptr; e.inj_stride = 0;
   memset(&e.aux, 0, sizeof(e.aux));
   CK(cudaStreamSynchronize(h->stream));
+  if (!tmaps_check(e)) return fail(BNR_ECUDA, "cuTensorMapEncodeTiled refused a tensor map of this problem's geometry");
   return BNR_OK;
 }
 

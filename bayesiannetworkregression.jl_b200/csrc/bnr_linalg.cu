@@ -1440,25 +1440,44 @@ bool tmap_setup() {
   return true;
 }
 // rows beyond `rows` (the box is 4 rows wider than a tile) and k-rows beyond `krows` read as zeros
-static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows,
-                            uint32_t box_k = SY_BK) {
-  CUtensorMap m;
-  memset(&m, 0, sizeof(m));
+static CUresult encode_map(CUtensorMap* m, const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows,
+                           uint32_t box_k) {
+  memset(m, 0, sizeof(*m));
   const cuuint64_t dims[2] = {rows, krows};
   const cuuint64_t strides[1] = {ld * sizeof(double)};
   const cuuint32_t box[2] = {box_rows, box_k};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = (tmap_setup() ? g_tmap_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box,
-                                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
-                             : CUDA_ERROR_NOT_SUPPORTED);
+  if (!tmap_setup()) return CUDA_ERROR_NOT_SUPPORTED;
+  return g_tmap_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+static CUtensorMap make_map(const double* base, uint64_t rows, uint64_t krows, uint64_t ld, uint32_t box_rows,
+                            uint32_t box_k = SY_BK) {
+  CUtensorMap m;
+  const CUresult r = encode_map(&m, base, rows, krows, ld, box_rows, box_k);
   if (r != CUDA_SUCCESS) {
-    // (bnr_create has already checked tmap_setup(); a failure here is a programming error of the caller's geometry)
+    // (bnr_create has already encoded every map of this handle's geometry, tmaps_check(): unreachable from the ABI)
     fprintf(stderr, "[bnr] cuTensorMapEncodeTiled failed (%d) for a %llu x %llu operand, box %u x %d\n", (int)r,
             (unsigned long long)rows, (unsigned long long)krows, box_rows, (int)box_k);
     abort();
   }
   return m;
+}
+// every tensor map the launchers will build for this handle, encoded once at creation so that a driver that refuses one
+// is reported through the ABI (bnr_create -> BNR_ECUDA) instead of at the first sweep
+bool tmaps_check(const Engine& e) {
+  const Dims& d = e.d;
+  const uint64_t N = d.gdim, C = d.C, T = d.gdim / SY_BT;
+  CUtensorMap m;
+  bool ok = true;
+  if (d.gmode != 2) ok = ok && encode_map(&m, e.X, d.np, d.qp, d.np, SY_LDS, SY_BK) == CUDA_SUCCESS;
+  for (uint32_t box : {(uint32_t)SY_LDS, (uint32_t)(SY_BT / 2 + 4), (uint32_t)(SY_BT / 4 + 4)})
+    ok = ok && encode_map(&m, e.G, N, N * C, N, box, SY_BK) == CUDA_SUCCESS;
+  ok = ok && encode_map(&m, e.Linv, SY_BT, SY_BT * T * C, SY_BT, SY_LDS, SY_BK) == CUDA_SUCCESS;
+  ok = ok && encode_map(&m, e.G, N, N * C, N, SY_BT, BW_COLS) == CUDA_SUCCESS;       // back solve
+  ok = ok && encode_map(&m, e.Linv, SY_BT, SY_BT * T * C, SY_BT, SY_BT, BW_COLS) == CUDA_SUCCESS;
+  return ok;
 }
 
 int syrk_splits(const Dims& d, int C) {
